@@ -1,0 +1,139 @@
+/*
+ * mmdp.h - C ABI of the B200-native MMaDA-Parallel denoising hot path (libmmdp.so).
+ *
+ * The reference (tyfeld/MMaDA-Parallel) has no FFI/plugin layer: its boundary is the Python API
+ *   generate_ti2ti(...)                         MMaDA-Parallel-A/generators/parallel_generator.py:102-368
+ *   model(input_ids, infer=True).logits         MMaDA-Parallel-A/model/modeling_xllmx_dimoo.py:41-72
+ *   MMadaModelLM.interleave_generate(...)       MMaDA-Parallel-M/models/modeling_mmada.py:118-248
+ *   MAGVITv2.decode_code(...)                   MMaDA-Parallel-M/models/modeling_magvitv2.py:429-433
+ * Every entry point below is what a ctypes stub under those callables binds; each comment
+ * names the reference lines the call replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; bf16 tensors are passed as uint16_t*;
+ *   - every function returns 0 on success, -1 on failure; mmdp_last_error() returns the (thread-local) message;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); no call synchronises the device;
+ *   - nothing here falls back to the CPU: without a CUDA device every compute call fails with an error.
+ */
+#ifndef MMDP_H_
+#define MMDP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMDP_VERSION 100
+#if defined(__GNUC__)
+#define MMDP_API __attribute__((visibility("default")))
+#else
+#define MMDP_API
+#endif
+
+MMDP_API int mmdp_version(void);
+MMDP_API const char* mmdp_last_error(void);
+
+/* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */
+#define MMDP_EPI_PLAIN 0   /* C = bf16(A W^T)                                 nn.Linear, modeling_llada.py:1402      */
+#define MMDP_EPI_RESID 1   /* C = bf16(bf16(A W^T) + R)                       attn_out :744 + :953; ff_out :968+:970  */
+#define MMDP_EPI_SWIGLU 3  /* C = bf16(bf16(silu(bf16 g)) * bf16 u), W rows interleaved 128 gate / 128 up   :962-967 */
+
+/* C[M,N] = A[M,K] * W[N,K]^T, bf16 in, fp32 accumulate (tcgen05/TMEM), fused epilogue.
+ * lda/ldw/ldc/ldr are row strides in elements (multiples of 8). For MMDP_EPI_SWIGLU, C has N/2 columns. */
+MMDP_API int mmdp_gemm_bf16(int epilogue, const uint16_t* A, int lda, const uint16_t* W, int ldw, int M, int N, int K,
+                   uint16_t* C, int ldc, const uint16_t* R, int ldr, void* stream);
+
+/* q/k/v projection + rotary embedding (modeling_llada.py:925-927, RotaryEmbedding :402-435).
+ * Wqkv = [q_proj; k_proj; v_proj] rows ([3*d_model, d_model]); A = normed activations [B*L, d_model].
+ * Outputs: q,k [B*L, d_model] with RoPE applied (fp32 math on the bf16-rounded projections, positions 0..L-1 per batch row);
+ * vt [B, n_heads, 128, Lpad] = V transposed (token index contiguous); columns >= L of vt must be zero (never written).
+ * cos/sin: fp32 [L, 64] tables (first half of the reference's cat(freqs, freqs) table). head_dim must be 128. */
+MMDP_API int mmdp_qkv_rope(const uint16_t* A, int lda, const uint16_t* Wqkv, int M, int d_model, int n_heads, int L, int Lpad,
+                  const float* cos_tab, const float* sin_tab, uint16_t* q, uint16_t* k, uint16_t* vt, void* stream);
+
+/* softmax(q k^T * scale) v, no mask, non-causal (F.scaled_dot_product_attention call at modeling_llada.py:672-679).
+ * q,k: [B*L, n_heads*128]; vt: [B, n_heads, 128, Lpad]; out: [B*L, n_heads*128]. */
+MMDP_API int mmdp_attention(const uint16_t* q, const uint16_t* k, const uint16_t* vt, uint16_t* out, int B, int n_heads, int L,
+                   int Lpad, float scale, void* stream);
+
+/* RMSLayerNorm.forward (modeling_llada.py:315-329). rows (nullable int32[M]) gathers input rows. */
+MMDP_API int mmdp_rmsnorm(const uint16_t* x, int ldx, const int32_t* rows, const uint16_t* weight, uint16_t* y, int ldy, int M,
+                 int d, float eps, void* stream);
+
+/* wte lookup (modeling_llada.py:1265): x[i,:] = wte[ids[i],:] */
+MMDP_API int mmdp_embed(const int64_t* ids, const uint16_t* wte, uint16_t* x, int M, int d, int64_t vocab, void* stream);
+
+/* ---- mask-predict step --------------------------------------------------------------------------------------- */
+
+/* Text step (parallel_generator.py:181-217; M: modeling_mmada.py:179-209).
+ * cond/uncond: logits rows of the R text positions ([R, ld] bf16). uncond nullable (A); with uncond the logits are
+ * cond + text_cfg*(uncond-cond) in bf16 (M). unoise nullable: torch.rand(dtype=bf16) noise [R, ld_noise] for A's
+ * add_gumbel_noise at `temperature` > 0. ids_text points at the R ids of the text span inside the sequence; the k
+ * most confident masked positions (fp64 softmax probability of the argmax token) are committed in place.
+ * x0_ws int64[R], conf_ws double[R] are caller-provided workspaces (also the debug outputs). */
+MMDP_API int mmdp_text_step(const uint16_t* cond, const uint16_t* uncond, int64_t ld, int R, int V, float text_cfg,
+                   const uint16_t* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
+                   int k, int64_t* x0_ws, double* conf_ws, void* stream);
+
+/* Image step (parallel_generator.py:220-344 for variant 0 = A; modeling_mmada.py:211-241 for variant 1 = M).
+ * cond/unc_a/unc_b: [N, ld] bf16 logits restricted to the C codebook columns.
+ *   A: logits = cond + s_a*(cond-unc_a) + s_b*(cond-unc_b)   (unc_a = uncond_text, unc_b = uncond_image; nullable)
+ *   M: logits = s_b*cond - s_a*unc_a                           (caller passes s_b = 1+image_cfg, s_a = image_cfg)
+ * qnoise nullable: Exp(1) noise [N, C] bf16 = the `q` torch.multinomial draws; null -> argmax(probs) (temperature 0).
+ * conf_noise nullable [N] bf16: A randn / M uniform noise of mask_by_random_topk; temp = temperature*(1-ratio).
+ * sched_len = floor(N * noise_schedule(ratio)) evaluated by the host exactly like the reference (fp32 torch scalar).
+ * ids: full sequence id buffer (int64) updated in place at positions pos[0..N); vq_offset = text vocab size.
+ * Workspaces/outputs: sampled_ws int32[N] (ids before re-masking = M's return value), selp_ws float[N],
+ * unknown_ws uint8[N]; probs_out (nullable, [N, C] bf16), mask_len_out (nullable int32), masking_out (nullable uint8[N]). */
+MMDP_API int mmdp_image_step(int variant, const uint16_t* cond, const uint16_t* unc_a, const uint16_t* unc_b, int64_t ld, int N,
+                    int C, float s_a, float s_b, const uint16_t* qnoise, const uint16_t* conf_noise, float temp,
+                    int sched_len, int64_t* ids, const int32_t* pos, int64_t mask_id, int64_t vq_offset,
+                    int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, uint16_t* probs_out,
+                    int32_t* mask_len_out, uint8_t* masking_out, void* stream);
+
+/* LFQuantizer.get_codebook_entry (modeling_magvitv2.py:208-221): ids [B, N] -> z_q fp32 [B, bits, N] (+-1). */
+MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, void* stream);
+
+/* ---- whole-model context (LLaDAModel.forward, modeling_llada.py:1201-1415) ----------------------------------- */
+typedef struct mmdp_model mmdp_model;
+
+typedef struct {
+    int32_t d_model;      /* 4096 */
+    int32_t n_heads;      /* 32, head_dim must be 128 */
+    int32_t n_layers;     /* 32 */
+    int32_t mlp_hidden;   /* 12288 = rows of ff_proj / up_proj */
+    int32_t vocab_size;   /* rows of wte and of the LM head (embedding_size) */
+    int32_t max_seq_len;  /* workspace sizing */
+    int32_t max_batch;    /* workspace sizing (CFG batch) */
+    float rms_eps;
+} mmdp_model_config;
+
+MMDP_API int mmdp_model_create(const mmdp_model_config* cfg, mmdp_model** out);
+MMDP_API void mmdp_model_destroy(mmdp_model* m);
+
+/* Copies (and packs) one tensor of the HF state dict into the model-owned device buffers. `src` may be a device or
+ * a pinned/pageable host pointer (cudaMemcpyDefault). Names (layer = 0..n_layers-1):
+ *   "wte" [V,d], "ln_f" [d], "head" [V,d],
+ *   "blocks.<i>.q_proj|k_proj|v_proj|attn_out" [d,d], "blocks.<i>.ff_proj|up_proj" [ff,d], "blocks.<i>.ff_out" [d,ff],
+ *   "blocks.<i>.attn_norm|ff_norm" [d]. */
+MMDP_API int mmdp_model_set_weight(mmdp_model* m, const char* name, const void* src, int64_t rows, int64_t cols, void* stream);
+
+/* fp32 rotary tables [L, 64] (cos, sin), computed by the host exactly like RotaryEmbedding.get_rotary_embedding. */
+MMDP_API int mmdp_model_set_rope(mmdp_model* m, const float* cos_tab, const float* sin_tab, int L, void* stream);
+
+/* One forward over ids [B, L]. Logits are produced only where requested:
+ *   full_logits   (nullable) [B*L, V]                      - the reference contract (model(...).logits)
+ *   rows_a/out_a  (nullable) n_a flattened row indices (b*L + pos) x all V columns      -> out_a [n_a, V]
+ *   rows_b/out_b  (nullable) n_b flattened row indices x columns [col0_b, col0_b+ncols_b) -> out_b [n_b, ncols_b] */
+MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16_t* full_logits, const int32_t* rows_a,
+                       int n_a, uint16_t* out_a, const int32_t* rows_b, int n_b, int col0_b, int ncols_b,
+                       uint16_t* out_b, void* stream);
+
+/* Debug/testing: copy of the residual stream after `layer` layers is kept when enabled (device pointer returned). */
+MMDP_API const uint16_t* mmdp_model_hidden(mmdp_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDP_H_ */

@@ -1,0 +1,293 @@
+// extern "C" surface (include/mmdp.h) and the native model context: device-resident packed weights, activation
+// workspace and the per-layer launch sequence of LLaDAModel.forward (MMaDA-Parallel-A/model/modeling_llada.py:1201-1415,
+// block :906-972). No torch types cross this boundary.
+#include "../../include/mmdp.h"
+#include "mmdp_internal.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+using namespace mmdp;
+typedef __nv_bfloat16 bf16;
+
+namespace mmdp {
+
+__global__ void lfq_kernel(const int64_t* __restrict__ ids, float* __restrict__ zq, int N, int bits) {
+    // z_q[b, c, n] = 2*((id >> (bits-1-c)) & 1) - 1     (LFQuantizer.__init__/get_codebook_entry, modeling_magvitv2.py:186-221)
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int64_t id = ids[(size_t)b * N + n];
+    for (int c = 0; c < bits; ++c) zq[((size_t)b * bits + c) * N + n] = ((id >> (bits - 1 - c)) & 1) ? 1.0f : -1.0f;
+}
+
+int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream_t stream) {
+    if (B <= 0 || N <= 0) return 0;
+    if (bits <= 0 || bits > 62) return set_error("lfq_decode: bits out of range");
+    dim3 grid((N + 255) / 256, B);
+    lfq_kernel<<<grid, 256, 0, stream>>>(ids, zq, N, bits);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mmdp
+
+struct LayerWeights {
+    bf16* wqkv;       // [3d, d]   rows: q_proj | k_proj | v_proj
+    bf16* wo;         // [d, d]
+    bf16* w13;        // [2ff, d]  128-row blocks interleaved: ff_proj block t, up_proj block t
+    bf16* w2;         // [d, ff]
+    bf16* attn_norm;  // [d]
+    bf16* ff_norm;    // [d]
+};
+
+struct mmdp_model {
+    mmdp_model_config cfg;
+    std::vector<LayerWeights> layers;
+    bf16* wte = nullptr;
+    bf16* ln_f = nullptr;
+    bf16* head = nullptr;
+    float* cos_tab = nullptr;
+    float* sin_tab = nullptr;
+    int rope_len = 0;
+    // workspace
+    int Mmax = 0, Lpad_max = 0;
+    bf16 *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *vt = nullptr, *att = nullptr, *h = nullptr, *xr = nullptr;
+    int vt_B = 0, vt_Lpad = 0;  // layout the vt buffer was last zeroed for
+    std::vector<void*> allocs;
+};
+
+static int dev_alloc(mmdp_model* m, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    m->allocs.push_back(*p);
+    return 0;
+}
+
+extern "C" {
+
+MMDP_API int mmdp_version(void) { return MMDP_VERSION; }
+MMDP_API const char* mmdp_last_error(void) { return last_error(); }
+
+MMDP_API int mmdp_gemm_bf16(int epilogue, const uint16_t* A, int lda, const uint16_t* W, int ldw, int M, int N, int K,
+                   uint16_t* C, int ldc, const uint16_t* R, int ldr, void* stream) {
+    if (epilogue != MMDP_EPI_PLAIN && epilogue != MMDP_EPI_RESID && epilogue != MMDP_EPI_SWIGLU)
+        return set_error("mmdp_gemm_bf16: unknown epilogue %d", epilogue);
+    return gemm_bf16(epilogue, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, (bf16*)C, ldc, (const bf16*)R, ldr,
+                     nullptr, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_qkv_rope(const uint16_t* A, int lda, const uint16_t* Wqkv, int M, int d_model, int n_heads, int L, int Lpad,
+                  const float* cos_tab, const float* sin_tab, uint16_t* q, uint16_t* k, uint16_t* vt, void* stream) {
+    QkvRopeArgs qa{(bf16*)q, (bf16*)k, (bf16*)vt, cos_tab, sin_tab, L, Lpad, d_model, n_heads};
+    return gemm_bf16(EPI_QKVROPE, (const bf16*)A, lda, (const bf16*)Wqkv, d_model, M, 3 * d_model, d_model, nullptr, 0,
+                     nullptr, 0, &qa, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_attention(const uint16_t* q, const uint16_t* k, const uint16_t* vt, uint16_t* out, int B, int n_heads, int L,
+                   int Lpad, float scale, void* stream) {
+    return attention_fwd((const bf16*)q, (const bf16*)k, (const bf16*)vt, (bf16*)out, B, n_heads, L, Lpad, scale,
+                         (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_rmsnorm(const uint16_t* x, int ldx, const int32_t* rows, const uint16_t* weight, uint16_t* y, int ldy, int M,
+                 int d, float eps, void* stream) {
+    return rmsnorm_rows((const bf16*)x, ldx, rows, (const bf16*)weight, (bf16*)y, ldy, M, d, eps, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_embed(const int64_t* ids, const uint16_t* wte, uint16_t* x, int M, int d, int64_t vocab, void* stream) {
+    return embed_rows(ids, (const bf16*)wte, (bf16*)x, M, d, vocab, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_text_step(const uint16_t* cond, const uint16_t* uncond, int64_t ld, int R, int V, float text_cfg,
+                   const uint16_t* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
+                   int k, int64_t* x0_ws, double* conf_ws, void* stream) {
+    return text_step((const bf16*)cond, (const bf16*)uncond, ld, R, V, text_cfg, (const bf16*)unoise, ld_noise,
+                     temperature, ids_text, mask_id, k, x0_ws, conf_ws, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_image_step(int variant, const uint16_t* cond, const uint16_t* unc_a, const uint16_t* unc_b, int64_t ld, int N,
+                    int C, float s_a, float s_b, const uint16_t* qnoise, const uint16_t* conf_noise, float temp,
+                    int sched_len, int64_t* ids, const int32_t* pos, int64_t mask_id, int64_t vq_offset,
+                    int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, uint16_t* probs_out,
+                    int32_t* mask_len_out, uint8_t* masking_out, void* stream) {
+    if (variant != 0 && variant != 1) return set_error("mmdp_image_step: variant must be 0 (A) or 1 (M)");
+    return image_step(variant, (const bf16*)cond, (const bf16*)unc_a, (const bf16*)unc_b, ld, N, C, s_a, s_b,
+                      (const bf16*)qnoise, (const bf16*)conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
+                      sampled_ws, selp_ws, unknown_ws, (bf16*)probs_out, mask_len_out, masking_out,
+                      (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, void* stream) {
+    return lfq_decode(ids, zq, B, N, bits, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// model context
+// ------------------------------------------------------------------------------------------------
+MMDP_API int mmdp_model_create(const mmdp_model_config* c, mmdp_model** out) {
+    if (!c || !out) return set_error("mmdp_model_create: null argument");
+    if (c->d_model != c->n_heads * 128) return set_error("mmdp_model_create: head_dim must be 128");
+    if (c->d_model % 256) return set_error("mmdp_model_create: d_model must be a multiple of 256");
+    if (c->mlp_hidden % 128) return set_error("mmdp_model_create: mlp_hidden must be a multiple of 128");
+    if (c->vocab_size % 8) return set_error("mmdp_model_create: vocab_size must be a multiple of 8");
+    if (c->n_layers <= 0 || c->max_seq_len <= 0 || c->max_batch <= 0) return set_error("mmdp_model_create: bad sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_error("mmdp_model_create: no CUDA device (this library has no CPU fallback)");
+    mmdp_model* m = new mmdp_model();
+    m->cfg = *c;
+    const size_t d = c->d_model, ff = c->mlp_hidden, V = c->vocab_size;
+    m->layers.resize(c->n_layers);
+    int rc = 0;
+    for (auto& l : m->layers) {
+        rc |= dev_alloc(m, (void**)&l.wqkv, 3 * d * d * 2);
+        rc |= dev_alloc(m, (void**)&l.wo, d * d * 2);
+        rc |= dev_alloc(m, (void**)&l.w13, 2 * ff * d * 2);
+        rc |= dev_alloc(m, (void**)&l.w2, d * ff * 2);
+        rc |= dev_alloc(m, (void**)&l.attn_norm, d * 2);
+        rc |= dev_alloc(m, (void**)&l.ff_norm, d * 2);
+    }
+    rc |= dev_alloc(m, (void**)&m->wte, V * d * 2);
+    rc |= dev_alloc(m, (void**)&m->head, V * d * 2);
+    rc |= dev_alloc(m, (void**)&m->ln_f, d * 2);
+    m->Mmax = c->max_batch * c->max_seq_len;
+    m->Lpad_max = ((c->max_seq_len + 127) / 128) * 128;
+    const size_t Mm = m->Mmax;
+    rc |= dev_alloc(m, (void**)&m->x, Mm * d * 2);
+    rc |= dev_alloc(m, (void**)&m->xn, Mm * d * 2);
+    rc |= dev_alloc(m, (void**)&m->q, Mm * d * 2);
+    rc |= dev_alloc(m, (void**)&m->k, Mm * d * 2);
+    rc |= dev_alloc(m, (void**)&m->att, Mm * d * 2);
+    rc |= dev_alloc(m, (void**)&m->xr, Mm * d * 2);
+    rc |= dev_alloc(m, (void**)&m->h, Mm * ff * 2);
+    rc |= dev_alloc(m, (void**)&m->vt, (size_t)c->max_batch * d * m->Lpad_max * 2);
+    rc |= dev_alloc(m, (void**)&m->cos_tab, (size_t)c->max_seq_len * 64 * 4);
+    rc |= dev_alloc(m, (void**)&m->sin_tab, (size_t)c->max_seq_len * 64 * 4);
+    if (rc) {
+        mmdp_model_destroy(m);
+        return -1;
+    }
+    *out = m;
+    return 0;
+}
+
+MMDP_API void mmdp_model_destroy(mmdp_model* m) {
+    if (!m) return;
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+}
+
+static int copy_rows(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    MMDP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+    return 0;
+}
+
+MMDP_API int mmdp_model_set_weight(mmdp_model* m, const char* name, const void* src, int64_t rows, int64_t cols, void* stream) {
+    if (!m || !name || !src) return set_error("mmdp_model_set_weight: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t d = m->cfg.d_model, ff = m->cfg.mlp_hidden, V = m->cfg.vocab_size;
+    auto expect = [&](int64_t r, int64_t c) -> int {
+        if (rows != r || cols != c)
+            return set_error("mmdp_model_set_weight(%s): expected [%lld,%lld], got [%lld,%lld]", name, (long long)r,
+                             (long long)c, (long long)rows, (long long)cols);
+        return 0;
+    };
+    const uint8_t* sb = (const uint8_t*)src;
+    if (!strcmp(name, "wte")) { if (expect(V, d)) return -1; return copy_rows(m->wte, src, V * d * 2, s); }
+    if (!strcmp(name, "head")) { if (expect(V, d)) return -1; return copy_rows(m->head, src, V * d * 2, s); }
+    if (!strcmp(name, "ln_f")) { if (expect(d, 1) && expect(1, d)) return -1; return copy_rows(m->ln_f, src, d * 2, s); }
+    int li = -1;
+    char sub[64];
+    if (sscanf(name, "blocks.%d.%63s", &li, sub) != 2 || li < 0 || li >= m->cfg.n_layers)
+        return set_error("mmdp_model_set_weight: unknown tensor name '%s'", name);
+    LayerWeights& l = m->layers[li];
+    if (!strcmp(sub, "q_proj") || !strcmp(sub, "k_proj") || !strcmp(sub, "v_proj")) {
+        if (expect(d, d)) return -1;
+        const int which = sub[0] == 'q' ? 0 : (sub[0] == 'k' ? 1 : 2);
+        return copy_rows(l.wqkv + (size_t)which * d * d, src, d * d * 2, s);
+    }
+    if (!strcmp(sub, "attn_out")) { if (expect(d, d)) return -1; return copy_rows(l.wo, src, d * d * 2, s); }
+    if (!strcmp(sub, "ff_out")) { if (expect(d, ff)) return -1; return copy_rows(l.w2, src, d * ff * 2, s); }
+    if (!strcmp(sub, "attn_norm")) { if (expect(d, 1) && expect(1, d)) return -1; return copy_rows(l.attn_norm, src, d * 2, s); }
+    if (!strcmp(sub, "ff_norm")) { if (expect(d, 1) && expect(1, d)) return -1; return copy_rows(l.ff_norm, src, d * 2, s); }
+    if (!strcmp(sub, "ff_proj") || !strcmp(sub, "up_proj")) {
+        if (expect(ff, d)) return -1;
+        const int up = sub[0] == 'u' ? 1 : 0;
+        // one 2-D copy: source block t (128 rows, contiguous 128*d) -> destination block 2t+up
+        MMDP_CUDA(cudaMemcpy2DAsync(l.w13 + (size_t)up * 128 * d, (size_t)256 * d * 2, sb, (size_t)128 * d * 2,
+                                    (size_t)128 * d * 2, (size_t)(ff / 128), cudaMemcpyDefault, s));
+        return 0;
+    }
+    return set_error("mmdp_model_set_weight: unknown tensor name '%s'", name);
+}
+
+MMDP_API int mmdp_model_set_rope(mmdp_model* m, const float* cos_tab, const float* sin_tab, int L, void* stream) {
+    if (!m || !cos_tab || !sin_tab) return set_error("mmdp_model_set_rope: null argument");
+    if (L <= 0 || L > m->cfg.max_seq_len) return set_error("mmdp_model_set_rope: L=%d exceeds max_seq_len=%d", L, m->cfg.max_seq_len);
+    cudaStream_t s = (cudaStream_t)stream;
+    MMDP_CUDA(cudaMemcpyAsync(m->cos_tab, cos_tab, (size_t)L * 64 * 4, cudaMemcpyDefault, s));
+    MMDP_CUDA(cudaMemcpyAsync(m->sin_tab, sin_tab, (size_t)L * 64 * 4, cudaMemcpyDefault, s));
+    m->rope_len = L;
+    return 0;
+}
+
+MMDP_API const uint16_t* mmdp_model_hidden(mmdp_model* m) { return m ? (const uint16_t*)m->x : nullptr; }
+
+MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16_t* full_logits, const int32_t* rows_a,
+                       int n_a, uint16_t* out_a, const int32_t* rows_b, int n_b, int col0_b, int ncols_b,
+                       uint16_t* out_b, void* stream) {
+    if (!m || !ids) return set_error("mmdp_model_forward: null argument");
+    const mmdp_model_config& c = m->cfg;
+    if (B <= 0 || B > c.max_batch || L <= 0 || L > c.max_seq_len)
+        return set_error("mmdp_model_forward: B=%d L=%d outside workspace (max_batch=%d max_seq_len=%d)", B, L, c.max_batch, c.max_seq_len);
+    if (L > m->rope_len) return set_error("mmdp_model_forward: rotary table covers %d positions, need %d", m->rope_len, L);
+    if (n_b > 0 && (col0_b < 0 || ncols_b <= 0 || col0_b + ncols_b > c.vocab_size || (ncols_b % 8) || (col0_b % 4)))
+        return set_error("mmdp_model_forward: bad column window [%d,+%d)", col0_b, ncols_b);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int d = c.d_model, ff = c.mlp_hidden, V = c.vocab_size, H = c.n_heads;
+    const int M = B * L;
+    const int Lpad = ((L + 7) / 8) * 8;
+    if (m->vt_Lpad != Lpad) {  // (indexing depends on Lpad only; batch rows are disjoint)
+        // pad columns of V^T must be zero (they meet P == 0 in the P·V MMA); re-zero when the layout changes
+        MMDP_CUDA(cudaMemsetAsync(m->vt, 0, (size_t)c.max_batch * d * m->Lpad_max * 2, s));
+        m->vt_B = B;
+        m->vt_Lpad = Lpad;
+    }
+    const float scale = 1.0f / sqrtf(128.0f);
+    if (embed_rows(ids, m->wte, m->x, M, d, V, s)) return -1;
+    QkvRopeArgs qa{m->q, m->k, m->vt, m->cos_tab, m->sin_tab, L, Lpad, d, H};
+    for (int li = 0; li < c.n_layers; ++li) {
+        const LayerWeights& l = m->layers[li];
+        if (rmsnorm(m->x, d, l.attn_norm, m->xn, d, M, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_QKVROPE, m->xn, d, l.wqkv, d, M, 3 * d, d, nullptr, 0, nullptr, 0, &qa, s)) return -1;
+        if (attention_fwd(m->q, m->k, m->vt, m->att, B, H, L, Lpad, scale, s)) return -1;
+        if (gemm_bf16(EPI_RESID, m->att, d, l.wo, d, M, d, d, m->x, d, m->x, d, nullptr, s)) return -1;
+        if (rmsnorm(m->x, d, l.ff_norm, m->xn, d, M, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_SWIGLU, m->xn, d, l.w13, d, M, 2 * ff, d, m->h, ff, nullptr, 0, nullptr, s)) return -1;
+        if (gemm_bf16(EPI_RESID, m->h, ff, l.w2, ff, M, d, ff, m->x, d, m->x, d, nullptr, s)) return -1;
+    }
+    if (full_logits) {
+        if (rmsnorm(m->x, d, m->ln_f, m->xn, d, M, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_PLAIN, m->xn, d, m->head, d, M, V, d, (bf16*)full_logits, V, nullptr, 0, nullptr, s)) return -1;
+    }
+    if (n_a > 0) {
+        if (!rows_a || !out_a) return set_error("mmdp_model_forward: rows_a/out_a null");
+        if (n_a > m->Mmax) return set_error("mmdp_model_forward: too many rows_a");
+        if (rmsnorm_rows(m->x, d, rows_a, m->ln_f, m->xr, d, n_a, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_PLAIN, m->xr, d, m->head, d, n_a, V, d, (bf16*)out_a, V, nullptr, 0, nullptr, s)) return -1;
+    }
+    if (n_b > 0) {
+        if (!rows_b || !out_b) return set_error("mmdp_model_forward: rows_b/out_b null");
+        if (n_a + n_b > m->Mmax) return set_error("mmdp_model_forward: too many rows_a + rows_b");
+        bf16* xr_b = m->xr + (size_t)n_a * d;
+        if (rmsnorm_rows(m->x, d, rows_b, m->ln_f, xr_b, d, n_b, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_PLAIN, xr_b, d, m->head + (size_t)col0_b * d, d, n_b, ncols_b, d, (bf16*)out_b, ncols_b, nullptr, 0, nullptr, s)) return -1;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// HBM-bound row kernels of the transformer forward: embedding gather (wte lookup, modeling_llada.py:1265)
+// and RMSLayerNorm (modeling_llada.py:315-329) with the reference's two bf16 rounding points:
+//   y = bf16( w * bf16( x_fp32 * rsqrt(mean(x_fp32^2) + eps) ) )
+#include "mmdp_internal.h"
+#include "ptx.cuh"
+
+namespace mmdp {
+
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ wte,
+                             __nv_bfloat16* __restrict__ x, int d, int64_t vocab) {
+    const int row = blockIdx.x;
+    int64_t id = ids[row];
+    if (id < 0 || id >= vocab) id = 0;  // torch would raise; ids are validated on the host, this only avoids OOB reads
+    const uint4* src = reinterpret_cast<const uint4*>(wte + (size_t)id * d);
+    uint4* dst = reinterpret_cast<uint4*>(x + (size_t)row * d);
+    for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, int M, int d, int64_t vocab,
+               cudaStream_t stream) {
+    if (d % 8) return set_error("embed: d must be a multiple of 8");
+    embed_kernel<<<M, 128, 0, stream>>>(ids, wte, x, d, vocab);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// One CTA per output row. rows == nullptr: input row = output row; else input row = rows[i] (gather).
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
+               const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int d, float eps) {
+    const int orow = blockIdx.x;
+    const int irow = rows ? rows[orow] : orow;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)irow * ldx);
+    const uint4* w4 = reinterpret_cast<const uint4*>(w);
+    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)orow * ldy);
+    const int nvec = d / 8;
+
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 v = src[i];
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+            ss = fmaf(a, a, ss);
+            ss = fmaf(b, b, ss);
+        }
+    }
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    const float var = tot / (float)d;
+    const float rstd = __frcp_rn(__fsqrt_rn(__fadd_rn(var, eps)));  // torch.rsqrt on CPU == 1/sqrt(x)
+
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 v = src[i];
+        const uint4 wv = w4[i];
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = bf16_round(__fmul_rn(bf16_lo(u[j]), rstd));
+            const float b = bf16_round(__fmul_rn(bf16_hi(u[j]), rstd));
+            o[j] = pack_bf16x2(__fmul_rn(bf16_lo(ww[j]), a), __fmul_rn(bf16_hi(ww[j]), b));
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
+                 int M, int d, float eps, cudaStream_t stream) {
+    if (M <= 0) return 0;
+    if ((d % 8) || (ldx % 8) || (ldy % 8)) return set_error("rmsnorm: d/ldx/ldy must be multiples of 8");
+    rmsnorm_kernel<<<M, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, d, eps);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy, int M, int d, float eps,
+            cudaStream_t stream) {
+    return rmsnorm_rows(x, ldx, nullptr, w, y, ldy, M, d, eps, stream);
+}
+
+}  // namespace mmdp

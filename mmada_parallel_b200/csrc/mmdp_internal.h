@@ -1,0 +1,62 @@
+// Internal (C++) declarations shared by the .cu translation units behind the C ABI in include/mmdp.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mmdp {
+
+enum Epilogue { EPI_PLAIN = 0, EPI_RESID = 1, EPI_QKVROPE = 2, EPI_SWIGLU = 3 };
+
+int set_error(const char* fmt, ...);  // records the message for mmdp_last_error(), returns -1
+const char* last_error();
+int num_sms();
+
+#define MMDP_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::mmdp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// 2-D bf16 tensor map: tensor [rows, cols] with row stride ld (elements), box [box_rows, box_cols],
+// 128-byte swizzle (box_cols must be 64), out-of-bounds elements read as zero.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_cols);
+
+struct QkvRopeArgs {
+    __nv_bfloat16* q;       // [B*L, d_model]   rotary applied, head h at columns [128h, 128h+128)
+    __nv_bfloat16* k;       // [B*L, d_model]   rotary applied
+    __nv_bfloat16* vt;      // [B, H, 128, Lpad] V transposed (token index contiguous); pad columns must stay zero
+    const float* cos_tab;   // [L, 64] fp32
+    const float* sin_tab;   // [L, 64] fp32
+    int L, Lpad, d_model, n_heads;
+};
+
+int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+              __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa,
+              cudaStream_t stream);
+
+int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+                  int H, int L, int Lpad, float scale, cudaStream_t stream);
+
+int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, int M, int d, int64_t vocab,
+               cudaStream_t stream);
+int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy, int M, int d, float eps,
+            cudaStream_t stream);
+int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
+                 int M, int d, float eps, cudaStream_t stream);
+
+int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int R, int V, float text_cfg,
+              const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
+              int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream);
+int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_a, const __nv_bfloat16* unc_b, int64_t ld,
+               int N, int C, float s_a, float s_b, const __nv_bfloat16* qnoise, const __nv_bfloat16* conf_noise,
+               float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset,
+               int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, __nv_bfloat16* probs_out,
+               int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream);
+int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream_t stream);
+
+}  // namespace mmdp

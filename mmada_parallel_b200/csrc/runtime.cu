@@ -1,0 +1,70 @@
+// Host runtime helpers: error reporting, device properties, TMA tensor-map construction.
+// libcuda is NOT linked: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint so the
+// library loads (and exports its symbols) on a CPU-only box; calling into it without a GPU fails loudly.
+#include "mmdp_internal.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace mmdp {
+
+static thread_local char g_err[1024] = "";
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        n = prop.multiProcessorCount;
+    }
+    return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_cols) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error("cuTensorMapEncodeTiled not available (no CUDA driver / no GPU)");
+    if (box_cols != 64) return set_error("tmap: box_cols must be 64 (one 128-byte swizzle atom)");
+    if (box_rows == 0 || box_rows > 256) return set_error("tmap: box_rows out of range");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%llu cols=%llu ld=%llu box=[%u,%u]", (int)r,
+                         base, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows,
+                         box_cols);
+    return 0;
+}
+
+}  // namespace mmdp

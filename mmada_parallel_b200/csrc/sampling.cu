@@ -1,0 +1,420 @@
+// The discrete-diffusion mask-predict step as HBM-bound kernels (warp-shuffle reductions, 16-byte loads):
+//   text step  : MMaDA-Parallel-A/generators/parallel_generator.py:181-217  (M: models/modeling_mmada.py:179-209)
+//   image step : MMaDA-Parallel-A/generators/parallel_generator.py:220-344  (M: models/modeling_mmada.py:211-241)
+//   remask     : parallel_generator.py:23-70 mask_by_random_topk (A, exact-k from a stable ascending sort)
+//                M/models/sampling.py:31-36 (M, strict '<' against the k-th smallest)
+// All random numbers are INPUTS (drawn by the host from the same torch.Generator calls the reference makes), so the
+// kernels are deterministic functions and can be checked bit-for-bit against the oracle.
+// bf16 rounding points of the reference (python-scalar * bf16 tensor -> bf16, etc.) are reproduced explicitly.
+#include "mmdp_internal.h"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace mmdp {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+// ------------------------------------------------------------------------------------------------
+// text step, kernel 1: per-row argmax (first index on ties), fp64 softmax confidence of the argmax token
+// ------------------------------------------------------------------------------------------------
+struct TextRowArgs {
+    const __nv_bfloat16* cond;    // [R, ld]
+    const __nv_bfloat16* uncond;  // nullable; M: logits = cond + cfg * (uncond - cond), every op rounded to bf16
+    const __nv_bfloat16* unoise;  // nullable; A gumbel: uniform noise [R, V] bf16 (torch.rand(dtype=bf16))
+    int64_t ld, ld_noise;
+    int V;
+    float cfg, temperature;
+    int64_t* x0;    // [R]
+    double* conf;   // [R]
+};
+
+__device__ __forceinline__ float text_logit(float c, float u, float cfg, bool has_uncond) {
+    if (!has_uncond) return c;
+    const float d = bf16_round(__fsub_rn(u, c));
+    const float s = bf16_round(__fmul_rn(d, cfg));
+    return bf16_round(__fadd_rn(c, s));
+}
+// logits + temperature * (-log(-log(u + 1e-10) + 1e-10)), all in bf16 (parallel_generator.py:8-20)
+__device__ __forceinline__ float gumbel_bf16(float logit, float u, float temperature) {
+    float t = bf16_round(__fadd_rn(u, 1e-10f));
+    t = bf16_round(logf(t));
+    t = -t;
+    t = bf16_round(__fadd_rn(t, 1e-10f));
+    t = bf16_round(logf(t));
+    t = -t;
+    t = bf16_round(__fmul_rn(t, temperature));
+    return bf16_round(__fadd_rn(logit, t));
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) text_rows_kernel(TextRowArgs a) {
+    const int row = blockIdx.x;
+    const uint4* c4 = reinterpret_cast<const uint4*>(a.cond + (size_t)row * a.ld);
+    const uint4* u4 = a.uncond ? reinterpret_cast<const uint4*>(a.uncond + (size_t)row * a.ld) : nullptr;
+    const uint4* n4 = a.unoise ? reinterpret_cast<const uint4*>(a.unoise + (size_t)row * a.ld_noise) : nullptr;
+    const int nvec = a.V / 8;
+    const bool has_u = u4 != nullptr, has_n = n4 != nullptr;
+
+    // pass 1: max of the (CFG-mixed) logits, argmax of the (optionally Gumbel-perturbed) logits
+    float mx = -INFINITY;         // softmax max (un-noised)
+    float best = -INFINITY;       // argmax key
+    int best_i = 0x7fffffff;
+    float best_logit = 0.f;       // un-noised logit at best_i
+    for (int i = threadIdx.x; i < nvec; i += kThreads) {
+        float c[8], u[8], n[8];
+        unpack8(c4[i], c);
+        if (has_u) unpack8(u4[i], u);
+        if (has_n) unpack8(n4[i], n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float l = text_logit(c[j], has_u ? u[j] : 0.f, a.cfg, has_u);
+            mx = fmaxf(mx, l);
+            const float key = has_n ? gumbel_bf16(l, n[j], a.temperature) : l;
+            if (key > best) { best = key; best_i = i * 8 + j; best_logit = l; }
+        }
+    }
+    __shared__ float s_f[kThreads / 32];
+    __shared__ float s_best[kThreads / 32];
+    __shared__ int s_idx[kThreads / 32];
+    __shared__ float s_bl[kThreads / 32];
+    __shared__ double s_d[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        const float ol = __shfl_xor_sync(0xffffffffu, best_logit, o);
+        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_logit = ol; }
+    }
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (ln == 0) { s_f[w] = mx; s_best[w] = best; s_idx[w] = best_i; s_bl[w] = best_logit; }
+    __syncthreads();
+    mx = s_f[0]; best = s_best[0]; best_i = s_idx[0]; best_logit = s_bl[0];
+    for (int i = 1; i < kThreads / 32; ++i) {
+        mx = fmaxf(mx, s_f[i]);
+        if (s_best[i] > best || (s_best[i] == best && s_idx[i] < best_i)) { best = s_best[i]; best_i = s_idx[i]; best_logit = s_bl[i]; }
+    }
+
+    // pass 2 (row now L2-resident): sum exp(l - max) in fp64 == F.softmax(logits.to(float64)) denominator
+    double sum = 0.0;
+    const double dmx = (double)mx;
+    for (int i = threadIdx.x; i < nvec; i += kThreads) {
+        float c[8], u[8];
+        unpack8(c4[i], c);
+        if (has_u) unpack8(u4[i], u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float l = text_logit(c[j], has_u ? u[j] : 0.f, a.cfg, has_u);
+            const double d = (double)l - dmx;
+            if (d > -64.0) sum += exp(d);  // exp(-64) < 2^-92: below half an ulp of any fp64 sum >= 1
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (ln == 0) s_d[w] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) tot += s_d[i];
+        a.x0[row] = best_i;
+        a.conf[row] = exp((double)best_logit - dmx) / tot;
+    }
+}
+
+// text step, kernel 2: confidence top-k (k largest, ties -> lower index) and commit into the id buffer
+__global__ void text_commit_kernel(const int64_t* __restrict__ x0, const double* __restrict__ conf, int64_t* ids, int R,
+                                   int64_t mask_id, int k) {
+    extern __shared__ double s_conf[];
+    const int i = threadIdx.x;
+    bool masked = false;
+    double c = -INFINITY;
+    if (i < R) {
+        masked = ids[i] == mask_id;
+        c = masked ? conf[i] : -INFINITY;
+        s_conf[i] = c;
+    }
+    __syncthreads();
+    if (i < R) {
+        int rank = 0;
+        for (int j = 0; j < R; ++j) {
+            const double cj = s_conf[j];
+            rank += (cj > c) || (cj == c && j < i);
+        }
+        if (rank < k && masked) ids[i] = x0[i];
+    }
+}
+
+int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int R, int V, float text_cfg,
+              const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
+              int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream) {
+    if (R <= 0) return 0;
+    if (R > 1024) return set_error("text_step: at most 1024 text positions");
+    if ((V % 8) || (ld % 8) || (unoise && (ld_noise % 8))) return set_error("text_step: V/ld must be multiples of 8");
+    TextRowArgs a{cond, uncond, unoise, ld, ld_noise, V, text_cfg, temperature, x0_ws, conf_ws};
+    text_rows_kernel<512><<<R, 512, 0, stream>>>(a);
+    MMDP_CUDA(cudaGetLastError());
+    const int threads = ((R + 31) / 32) * 32;
+    text_commit_kernel<<<1, threads, R * sizeof(double), stream>>>(x0_ws, conf_ws, ids_text, R, mask_id, k);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// image step, kernel 1: per VQ position: CFG mix -> softmax (bf16 probs) -> argmax | exponential-race sample
+// ------------------------------------------------------------------------------------------------
+struct ImageRowArgs {
+    const __nv_bfloat16* cond;   // row r at cond + r*ld, `C` codebook logits
+    const __nv_bfloat16* unc_a;  // A: uncond_text (scale s_a) | M: uncond (scale s_a = image_cfg)
+    const __nv_bfloat16* unc_b;  // A: uncond_image (scale s_b) | M: unused
+    int64_t ld;
+    int C;           // codebook size (multiple of 8, <= 8192)
+    int variant;     // 0 = A, 1 = M
+    float s_a, s_b;
+    const __nv_bfloat16* qnoise;  // nullable: Exp(1) noise [N, C] bf16 (torch.multinomial's q); null -> argmax(probs)
+    const int64_t* ids;           // full id buffer
+    const int* pos;               // [N] sequence position of VQ token r
+    int64_t mask_id, vq_offset;
+    int clamp_known;              // A clamps known ids into [0, C-1]; M does not
+    int32_t* sampled;             // [N] out: where(unknown, sample, known)
+    float* selp;                  // [N] out: prob of the chosen id as bf16 value (or bf16 finfo.max for known)
+    uint8_t* unknown;             // [N] out
+    __nv_bfloat16* probs_out;     // nullable debug: [N, C]
+};
+
+static constexpr int kImgThreads = 256;
+static constexpr int kImgMaxPer = 4;  // 256 threads * 4 vec8 = 8192 columns
+
+__global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a) {
+    const int r = blockIdx.x;
+    const int nvec = a.C / 8;
+    const uint4* c4 = reinterpret_cast<const uint4*>(a.cond + (size_t)r * a.ld);
+    const uint4* ua4 = a.unc_a ? reinterpret_cast<const uint4*>(a.unc_a + (size_t)r * a.ld) : nullptr;
+    const uint4* ub4 = a.unc_b ? reinterpret_cast<const uint4*>(a.unc_b + (size_t)r * a.ld) : nullptr;
+
+    float x[kImgMaxPer][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < kImgMaxPer; ++t) {
+        const int i = threadIdx.x + t * kImgThreads;
+        if (i < nvec) {
+            float c[8], ua[8], ub[8];
+            unpack8(c4[i], c);
+            if (ua4) unpack8(ua4[i], ua);
+            if (ub4) unpack8(ub4[i], ub);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float l = c[j];
+                if (a.variant == 0) {
+                    // image_logits = cond; += s_t * (cond - unc_t); += s_i * (cond - unc_i)   (bf16 at every op)
+                    if (ua4 && a.s_a != 0.f) l = bf16_round(__fadd_rn(l, bf16_round(__fmul_rn(bf16_round(__fsub_rn(c[j], ua[j])), a.s_a))));
+                    if (ub4 && a.s_b != 0.f) l = bf16_round(__fadd_rn(l, bf16_round(__fmul_rn(bf16_round(__fsub_rn(c[j], ub[j])), a.s_b))));
+                } else {
+                    // (1 + s) * cond - s * uncond   (s_b carries the host-evaluated python float 1 + s)
+                    const float p1 = bf16_round(__fmul_rn(c[j], a.s_b));
+                    const float p2 = bf16_round(__fmul_rn(ua[j], a.s_a));
+                    l = bf16_round(__fsub_rn(p1, p2));
+                }
+                x[t][j] = l;
+                mx = fmaxf(mx, l);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[t][j] = -INFINITY;
+        }
+    }
+    __shared__ float s_f[kImgThreads / 32];
+    __shared__ int s_i[kImgThreads / 32];
+    __shared__ float s_p[kImgThreads / 32];
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (ln == 0) s_f[w] = mx;
+    __syncthreads();
+    mx = s_f[0];
+    for (int i = 1; i < kImgThreads / 32; ++i) mx = fmaxf(mx, s_f[i]);
+    __syncthreads();
+
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < kImgMaxPer; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float e = expf(__fsub_rn(x[t][j], mx));
+            x[t][j] = e;
+            sum += e;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (ln == 0) s_f[w] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int i = 0; i < kImgThreads / 32; ++i) sum += s_f[i];
+
+    // probs (bf16), then the sampling key: argmax(probs) or argmax(bf16(probs / q))
+    const int64_t tok = a.ids[a.pos[r]];
+    const bool unk = tok == a.mask_id;
+    const uint4* q4 = a.qnoise ? reinterpret_cast<const uint4*>(a.qnoise + (size_t)r * a.C) : nullptr;
+    float best = -INFINITY, best_p = 0.f;
+    int best_i = 0x7fffffff;
+    int64_t known = tok - a.vq_offset;
+    if (a.clamp_known) known = known < 0 ? 0 : (known > a.C - 1 ? a.C - 1 : known);
+    float known_p = 0.f;
+#pragma unroll
+    for (int t = 0; t < kImgMaxPer; ++t) {
+        const int i = threadIdx.x + t * kImgThreads;
+        if (i < nvec) {
+            float q[8];
+            if (q4) unpack8(q4[i], q);
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = bf16_round(__fdiv_rn(x[t][j], sum));
+                x[t][j] = p;
+                const float key = q4 ? bf16_round(__fdiv_rn(p, q[j])) : p;
+                if (key > best) { best = key; best_i = i * 8 + j; best_p = p; }
+                if (!unk && (int64_t)(i * 8 + j) == known) known_p = p;
+            }
+            if (a.probs_out) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(x[t][2 * j], x[t][2 * j + 1]);
+                reinterpret_cast<uint4*>(a.probs_out + (size_t)r * a.C)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+    (void)known_p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        const float op = __shfl_xor_sync(0xffffffffu, best_p, o);
+        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_p = op; }
+    }
+    if (ln == 0) { s_f[w] = best; s_i[w] = best_i; s_p[w] = best_p; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kImgThreads / 32; ++i)
+            if (s_f[i] > best || (s_f[i] == best && s_i[i] < best_i)) { best = s_f[i]; best_i = s_i[i]; best_p = s_p[i]; }
+        int samp = best_i;
+        if (samp > a.C - 1) samp = a.C - 1;  // also covers the (all-NaN) nothing-selected case
+        a.unknown[r] = unk ? 1 : 0;
+        if (unk) {
+            a.sampled[r] = samp;
+            a.selp[r] = best_p;
+        } else {
+            a.sampled[r] = (int32_t)known;
+            a.selp[r] = 3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).max
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// image step, kernel 2 (single CTA): confidence jitter -> stable rank -> re-mask -> write ids
+// ------------------------------------------------------------------------------------------------
+struct RemaskArgs {
+    int N;                 // number of VQ tokens (<= 1024)
+    int variant;           // 0 = A, 1 = M
+    const int32_t* sampled;
+    const float* selp;
+    const uint8_t* unknown;
+    const __nv_bfloat16* noise;  // A: randn [N] bf16 ; M: uniform [N] bf16 ; nullable when temp == 0
+    float temp;                  // temperature * (1 - ratio)
+    int sched_len;               // floor(N * noise_schedule(ratio)) evaluated on the host exactly as the reference does
+    int64_t* ids;
+    const int* pos;
+    int64_t mask_id, vq_offset;
+    int32_t* mask_len_out;       // nullable debug
+    uint8_t* masking_out;        // nullable debug [N]
+};
+
+__device__ __forceinline__ float log_bf16(float x) { return bf16_round(logf(x)); }
+
+__global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
+    __shared__ float s_conf[1024];
+    __shared__ int s_cnt[32];
+    __shared__ float s_cut;
+    const int i = threadIdx.x;
+    const bool in = i < a.N;
+    const int unk = in ? a.unknown[i] : 0;
+    int cnt = unk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((i & 31) == 0) s_cnt[i >> 5] = cnt;
+    float conf = INFINITY;
+    if (in) {
+        const float p = a.selp[i];
+        const float nz = a.noise ? __bfloat162float(a.noise[i]) : 0.f;
+        if (a.variant == 0) {
+            // confidence = log(probs + 1e-10) + temperature * noise     (parallel_generator.py:36)
+            const float lp = log_bf16(bf16_round(__fadd_rn(p, 1e-10f)));
+            const float tn = a.noise ? bf16_round(__fmul_rn(nz, a.temp)) : 0.f;
+            conf = bf16_round(__fadd_rn(lp, tn));
+        } else {
+            // confidence = log(clamp(p,1e-20)) + temperature * (-log(clamp(-log(clamp(u,1e-20)),1e-20)))  (sampling.py:9-16,31-32)
+            const float lp = log_bf16(fmaxf(p, bf16_round(1e-20f)));
+            float g = 0.f;
+            if (a.noise) {
+                g = log_bf16(fmaxf(nz, bf16_round(1e-20f)));
+                g = -g;
+                g = log_bf16(fmaxf(g, bf16_round(1e-20f)));
+                g = -g;
+            }
+            const float tn = bf16_round(__fmul_rn(g, a.temp));
+            conf = bf16_round(__fadd_rn(lp, tn));
+        }
+    }
+    s_conf[i] = conf;
+    __syncthreads();
+    int unknown_cnt = 0;
+    for (int j = 0; j < 32; ++j) unknown_cnt += s_cnt[j];
+    // mask_len = max(1, min(unknown - 1, sched_len))
+    int k = a.sched_len < unknown_cnt - 1 ? a.sched_len : unknown_cnt - 1;
+    if (k < 1) k = 1;
+    if (a.variant == 0) { if (k > a.N - 1) k = a.N - 1; if (k < 0) k = 0; }  // mask_by_random_topk clamps to [0, N-1]
+    int rank = 0;
+    if (in) {
+        for (int j = 0; j < a.N; ++j) {
+            const float cj = s_conf[j];
+            rank += (cj < conf) || (cj == conf && j < i);  // stable ascending sort position
+        }
+    }
+    bool masking = false;
+    if (a.variant == 0) {
+        masking = in && rank < k;
+    } else {
+        if (in && rank == (k < a.N ? k : a.N - 1)) s_cut = conf;  // sorted_confidence[mask_len]
+        __syncthreads();
+        masking = in && conf < s_cut;
+    }
+    if (in) {
+        a.ids[a.pos[i]] = masking ? a.mask_id : (int64_t)a.sampled[i] + a.vq_offset;
+        if (a.masking_out) a.masking_out[i] = masking ? 1 : 0;
+    }
+    if (i == 0 && a.mask_len_out) *a.mask_len_out = k;
+}
+
+int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_a, const __nv_bfloat16* unc_b, int64_t ld,
+               int N, int C, float s_a, float s_b, const __nv_bfloat16* qnoise, const __nv_bfloat16* conf_noise,
+               float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset,
+               int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, __nv_bfloat16* probs_out,
+               int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream) {
+    if (N <= 0 || N > 1024) return set_error("image_step: N must be in [1, 1024]");
+    if (C <= 0 || (C % 8) || C > kImgThreads * kImgMaxPer * 8) return set_error("image_step: codebook size must be a multiple of 8 and <= 8192");
+    if (ld % 8) return set_error("image_step: ld must be a multiple of 8");
+    if (variant == 1 && !unc_a) return set_error("image_step: variant M needs uncond logits");
+    ImageRowArgs ra{cond, unc_a, unc_b, ld, C, variant, s_a, s_b, qnoise, ids, pos, mask_id, vq_offset,
+                    variant == 0 ? 1 : 0, sampled_ws, selp_ws, unknown_ws, probs_out};
+    image_rows_kernel<<<N, kImgThreads, 0, stream>>>(ra);
+    MMDP_CUDA(cudaGetLastError());
+    RemaskArgs ma{N, variant, sampled_ws, selp_ws, unknown_ws, conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
+                  mask_len_out, masking_out};
+    image_remask_kernel<<<1, 1024, 0, stream>>>(ma);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mmdp
