@@ -1,0 +1,148 @@
+"""ORACLE (test infrastructure, NOT product code): CPU restatement of the two generation loops.
+
+  generate_ti2ti       restates MMaDA-Parallel-A/generators/parallel_generator.py:102-368
+  interleave_generate  restates MMaDA-Parallel-M/models/modeling_mmada.py:118-248
+The per-step arithmetic lives in oracle/sampling.py; this file restates the orchestration (schedules, which forwards
+run, how ids are rewritten). The python `.item()` loops of the reference are replaced by tensor indexing with the
+same results. Random draws come from sampling.NoiseSource (same calls, same order as the reference).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import sampling as S
+
+
+@torch.no_grad()
+def generate_ti2ti(model, input_ids, text_start, text_end, image_start, seq_len, newline_every, text_steps=100,
+                   text_gen_length=256, text_block_length=64, timesteps=100, temperature=1.0, text_temperature=0.7,
+                   cfg_scale=0.0, cfg_img=4.0, uncon_text=None, uncon_image=None, tokenizer=None,
+                   remasking="low_confidence", noise_schedule=S.cosine_schedule, generator=None,
+                   text_vocab_size=126356, codebook_size=8192, trace: Optional[list] = None,
+                   final_fill: Optional[torch.Tensor] = None, stable_sort: bool = False):
+    """Returns (image_tokens: List[int], text_tokens: List[int] | str). `final_fill` (optional int tensor) supplies
+    the values the reference draws with torch.randint on the GLOBAL CPU RNG for still-masked image tokens (:362);
+    when None the global RNG is used exactly like the reference."""
+    if remasking != "low_confidence":
+        raise NotImplementedError(remasking)
+    MASK, NL = S.MASK_TOKEN_A, S.NEW_LINE_A
+    ids = input_ids.clone()                                                       # :140
+    total_image_len = seq_len + seq_len // newline_every
+    image_end = image_start + total_image_len
+    n_masked = int((ids[0, text_start:text_end] == MASK).sum())
+    num_transfer = S.get_num_transfer_tokens_a(n_masked, text_steps)               # :153-154 (batch row 0)
+    img_steps = S.image_step_indices(text_steps, timesteps)                       # :157-159
+    pos_map = [i for i in range(image_start, image_end) if int(ids[0, i]) != NL]   # :164-167
+    assert len(pos_map) == seq_len, f"Expected {seq_len} VQ tokens, got {len(pos_map)}"
+    pos = torch.tensor(pos_map, dtype=torch.long)
+    noise = S.NoiseSource(generator, dtype=torch.bfloat16)
+    dtype = None
+    for step in range(text_steps):
+        cond_logits = model(ids, infer=True, use_cache=False).logits               # :178
+        dtype = cond_logits.dtype
+        noise.dtype = dtype
+        text_ids = ids[0, text_start:text_end]
+        if int((text_ids == MASK).sum()) > 0:                                      # :183
+            tl = cond_logits[0, text_start:text_end, :]
+            un = noise.text_uniform((1,) + tuple(tl.shape))[0].to(tl.device) if text_temperature != 0 else None
+            new_ids, x0, conf = S.text_step(tl, text_ids, MASK, num_transfer[step], temperature=text_temperature,
+                                            uniform_noise=un)
+            ids[0, text_start:text_end] = new_ids
+        rec = {"step": step, "ids_after_text": ids[0].clone()}
+        if step in img_steps:                                                      # :220
+            tok = ids[0, pos]
+            vq = torch.where(tok == MASK, torch.tensor(-1), torch.clamp(tok - text_vocab_size, 0, codebook_size - 1))
+            sl = slice(text_vocab_size, text_vocab_size + codebook_size)
+            cond_vq = cond_logits[0, pos][:, sl]
+            unc_t = unc_i = None
+            if (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None):  # :243
+                ids_t, ids_i = ids.clone(), ids.clone()
+                if uncon_text is not None:
+                    ids_t[:, : uncon_text.shape[1]] = uncon_text
+                if uncon_image is not None:
+                    ids_i[:, : uncon_image.shape[1]] = uncon_image
+                # the reference runs both forwards (:263-264); the uncond_text result is unused when cfg_scale == 0
+                if cfg_scale != 0.0:
+                    unc_t = model(ids_t, infer=True, use_cache=False).logits[0, pos][:, sl]
+                unc_i = model(ids_i, infer=True, use_cache=False).logits[0, pos][:, sl]
+            else:
+                unc_t = torch.zeros_like(cond_vq)                                  # :277-278
+                unc_i = torch.zeros_like(cond_vq)
+            q = noise.multinomial_q(seq_len, codebook_size).to(cond_vq.device) if temperature != 0 else None
+            ratio = 1.0 * (step + 1) / text_steps
+            img_temp = temperature * (1.0 - ratio)                                 # :330
+            rn = noise.remask_randn((1, seq_len))[0].to(cond_vq.device)            # :333 -> :30-31 (always drawn)
+            out = S.image_step("A", cond_vq, unc_t, unc_i, cfg_scale, cfg_img, vq, MASK,
+                               S.sched_len(seq_len, step, text_steps, noise_schedule), img_temp, q, rn, codebook_size,
+                               stable=stable_sort)
+            fin = out["final"]
+            ids[0, pos] = torch.where(fin == -1, torch.tensor(MASK), fin + text_vocab_size)   # :339-344
+            rec.update(mask_len=out["mask_len"], sampled=out["sampled"].clone(), ids_after_image=ids[0].clone())
+        if trace is not None:
+            trace.append(rec)
+    text_tokens = [t for t in ids[0, text_start:text_end].tolist() if t != MASK]    # :348-349
+    generated_text = tokenizer.decode(text_tokens, skip_special_tokens=True) if tokenizer is not None else text_tokens
+    image_tokens, fill_i = [], 0
+    for t in ids[0, pos].tolist():                                                 # :353-362
+        if t != MASK:
+            image_tokens.append(max(0, min(t - text_vocab_size, codebook_size - 1)))
+        elif final_fill is not None:
+            image_tokens.append(int(final_fill[fill_i]))
+            fill_i += 1
+        else:
+            image_tokens.append(int(torch.randint(0, codebook_size, (1,)).item()))
+    return image_tokens, generated_text
+
+
+@torch.no_grad()
+def interleave_generate(model, input_ids, uncond_input_ids, text_cfg, image_cfg, text_steps, image_steps, soi_id, eoi_id,
+                        bos_id, mask_id, num_vq_tokens, codebook_size, max_seq_length, text_vocab_len,
+                        noise_schedule=S.cosine_schedule, generator=None, text_temperature=0.0,
+                        image_temperature=1.0, trace: Optional[list] = None):
+    """Restates MMadaModelLM.interleave_generate (modeling_mmada.py:118-248) with the config/tokenizer look-ups
+    (reserved_token_mapping, config.model.mmada.*, len(uni_prompting.text_tokenizer)) passed as plain integers.
+    `model(ids[B,L]).logits`. Returns (image ids [1, num_vq_tokens] (pre-remask sample), text ids [1, max_seq_length])."""
+    if not (text_cfg or image_cfg):
+        raise ValueError("text_cfg and image_cfg cannot be both 0")
+    if text_temperature != 0:
+        raise NotImplementedError("M add_gumbel_noise draws from the global RNG (modeling_mmada.py:56); not replayable")
+    inp, unc = input_ids.unsqueeze(0), uncond_input_ids.unsqueeze(0)
+    out_ids = torch.cat([torch.full((1, 1), soi_id), torch.full((1, num_vq_tokens), mask_id), torch.full((1, 1), eoi_id),
+                         torch.full((1, 1), bos_id), torch.full((1, max_seq_length - 1), mask_id)], dim=1)  # :142-148
+    ids = torch.cat([inp, out_ids], dim=1)
+    P = inp.shape[1]
+    n_masked = int((ids[:, -max_seq_length:] == mask_id).sum())
+    num_transfer = S.get_num_transfer_tokens_m(n_masked, text_steps)
+    img_idx = S.image_step_indices(text_steps, image_steps)
+    noise = S.NoiseSource(generator)
+    sampled_ids = None
+    isl = slice(P + 1, P + 1 + num_vq_tokens)
+    csl = slice(text_vocab_len, text_vocab_len + codebook_size)
+    for i in range(text_steps):
+        unc_ids = torch.cat([unc, ids[:, P:]], dim=1)                                # :166-169
+        logits = model(torch.cat([ids, unc_ids], dim=0)).logits                     # :172  (B = 2)
+        noise.dtype = logits.dtype
+        cond_logits, uncond_logits = torch.chunk(logits, 2, dim=0)
+        new_ids, x0, conf = S.text_step(cond_logits[0, -max_seq_length:], ids[0, -max_seq_length:], mask_id,
+                                        num_transfer[i], uncond_logits=uncond_logits[0, -max_seq_length:],
+                                        text_cfg=text_cfg)
+        ids[0, -max_seq_length:] = new_ids
+        rec = {"step": i, "ids_after_text": ids[0].clone()}
+        if i in img_idx:                                                             # :211
+            tok = ids[0, isl]
+            vq = torch.where(tok == mask_id, torch.tensor(mask_id), tok - text_vocab_len)   # :213-214
+            q = noise.multinomial_q(num_vq_tokens, codebook_size)
+            ratio = 1.0 * (i + 1) / text_steps
+            temp = image_temperature * (1.0 - ratio)
+            un = noise.remask_uniform((1, num_vq_tokens))[0]
+            out = S.image_step("M", cond_logits[0, isl][:, csl], uncond_logits[0, isl][:, csl], None, image_cfg, 0.0, vq,
+                               mask_id, S.sched_len(num_vq_tokens, i, text_steps, noise_schedule), temp, q, un,
+                               codebook_size)
+            sampled_ids = out["sampled"].unsqueeze(0)
+            ids[0, isl] = torch.where(out["masking"], torch.tensor(mask_id), out["sampled"] + text_vocab_len)  # :238
+            rec.update(mask_len=out["mask_len"], sampled=out["sampled"].clone(), ids_after_image=ids[0].clone())
+        if trace is not None:
+            trace.append(rec)
+    return sampled_ids, ids[:, -max_seq_length:]
