@@ -92,6 +92,13 @@ MMDP_API int mmdp_image_step(int variant, const uint16_t* cond, const uint16_t* 
                     int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, uint16_t* probs_out,
                     int32_t* mask_len_out, uint8_t* masking_out, void* stream);
 
+/* Second half of the image step on its own (mask_by_random_topk + write-back): parallel_generator.py:23-70, :318-344;
+ * M/models/sampling.py:31-36. Inputs are the per-token outputs of the first half (sampled ids, selected probabilities
+ * as bf16-representable floats, unknown flags). Ties between equal confidences keep the lower index masked first. */
+MMDP_API int mmdp_image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
+                      const uint16_t* conf_noise, float temp, int sched_len, int64_t* ids, const int32_t* pos,
+                      int64_t mask_id, int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, void* stream);
+
 /* LFQuantizer.get_codebook_entry (modeling_magvitv2.py:208-221): ids [B, N] -> z_q fp32 [B, bits, N] (+-1). */
 MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, void* stream);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
         _i,
         [_i, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _f, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     ),
+    "mmdp_image_remask": (_i, [_i, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "mmdp_lfq_decode": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mmdp_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "mmdp_model_destroy": (None, [_vp]),

@@ -121,6 +121,14 @@ MMDP_API int mmdp_image_step(int variant, const uint16_t* cond, const uint16_t* 
                       (cudaStream_t)stream);
 }
 
+MMDP_API int mmdp_image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
+                      const uint16_t* conf_noise, float temp, int sched_len, int64_t* ids, const int32_t* pos,
+                      int64_t mask_id, int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, void* stream) {
+    if (variant != 0 && variant != 1) return set_error("mmdp_image_remask: variant must be 0 (A) or 1 (M)");
+    return image_remask(variant, N, sampled, selp, unknown, (const bf16*)conf_noise, temp, sched_len, ids, pos, mask_id,
+                        vq_offset, mask_len_out, masking_out, (cudaStream_t)stream);
+}
+
 MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, void* stream) {
     return lfq_decode(ids, zq, B, N, bits, (cudaStream_t)stream);
 }

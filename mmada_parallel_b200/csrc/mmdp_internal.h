@@ -57,6 +57,9 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
                float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset,
                int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, __nv_bfloat16* probs_out,
                int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream);
+int image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
+                 const __nv_bfloat16* conf_noise, float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id,
+                 int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream);
 int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream_t stream);
 
 }  // namespace mmdp

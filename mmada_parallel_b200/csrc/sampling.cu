@@ -263,7 +263,6 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
     int best_i = 0x7fffffff;
     int64_t known = tok - a.vq_offset;
     if (a.clamp_known) known = known < 0 ? 0 : (known > a.C - 1 ? a.C - 1 : known);
-    float known_p = 0.f;
 #pragma unroll
     for (int t = 0; t < kImgMaxPer; ++t) {
         const int i = threadIdx.x + t * kImgThreads;
@@ -277,7 +276,6 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
                 x[t][j] = p;
                 const float key = q4 ? bf16_round(__fdiv_rn(p, q[j])) : p;
                 if (key > best) { best = key; best_i = i * 8 + j; best_p = p; }
-                if (!unk && (int64_t)(i * 8 + j) == known) known_p = p;
             }
             if (a.probs_out) {
 #pragma unroll
@@ -286,7 +284,6 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
             }
         }
     }
-    (void)known_p;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -397,6 +394,17 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
     if (i == 0 && a.mask_len_out) *a.mask_len_out = k;
 }
 
+int image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
+                 const __nv_bfloat16* conf_noise, float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id,
+                 int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream) {
+    if (N <= 0 || N > 1024) return set_error("image_remask: N must be in [1, 1024]");
+    RemaskArgs ma{N, variant, sampled, selp, unknown, conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
+                  mask_len_out, masking_out};
+    image_remask_kernel<<<1, 1024, 0, stream>>>(ma);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_a, const __nv_bfloat16* unc_b, int64_t ld,
                int N, int C, float s_a, float s_b, const __nv_bfloat16* qnoise, const __nv_bfloat16* conf_noise,
                float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset,
@@ -410,11 +418,8 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
                     variant == 0 ? 1 : 0, sampled_ws, selp_ws, unknown_ws, probs_out};
     image_rows_kernel<<<N, kImgThreads, 0, stream>>>(ra);
     MMDP_CUDA(cudaGetLastError());
-    RemaskArgs ma{N, variant, sampled_ws, selp_ws, unknown_ws, conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
-                  mask_len_out, masking_out};
-    image_remask_kernel<<<1, 1024, 0, stream>>>(ma);
-    MMDP_CUDA(cudaGetLastError());
-    return 0;
+    return image_remask(variant, N, sampled_ws, selp_ws, unknown_ws, conf_noise, temp, sched_len, ids, pos, mask_id,
+                        vq_offset, mask_len_out, masking_out, stream);
 }
 
 }  // namespace mmdp

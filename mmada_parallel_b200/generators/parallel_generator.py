@@ -1,0 +1,206 @@
+"""Drop-in for MMaDA-Parallel-A/generators/parallel_generator.py: same function names, signatures and return values.
+
+`generate_ti2ti` keeps the reference's control flow (:102-368) but every per-step computation is a CUDA kernel of
+libmmdp.so and the id sequence never leaves the GPU inside the loop:
+  forward (restricted LM head)      -> mmdp_model_forward   (text rows x V, image rows x codebook columns only)
+  text step   (:181-217)            -> mmdp_text_step       (argmax, fp64 softmax confidence, top-k commit)
+  image step  (:220-344)            -> mmdp_image_step      (CFG mix, softmax, sample, confidence, re-mask, write-back)
+The ~3 300 host<->device syncs per image step of the reference (.item() loops) are gone: the only host work per step
+is launching kernels and, when sampling is stochastic, drawing the noise tensors from the caller's torch.Generator
+with exactly the calls the reference makes (so a given seed selects the same random stream).
+
+Order of operations is the reference's: the conditional forward sees the ids BEFORE the text step of that iteration,
+the unconditional forwards see them AFTER it (parallel_generator.py:178, :217, :243-264), hence they are separate
+forwards. The uncond_text forward is skipped when cfg_scale == 0 (its logits are unused there, :286-287).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from .. import _lib
+from .._lib import check, lib, ptr, stream_ptr
+from ..schedule import (cosine_schedule, get_num_transfer_tokens as _num_transfer_row, image_generation_step_indices,
+                        scheduled_mask_len)
+
+MASK_TOKEN = 126336
+NEW_LINE = 126084
+
+__all__ = ["generate_ti2ti", "cosine_schedule", "get_num_transfer_tokens", "add_gumbel_noise", "mask_by_random_topk"]
+
+
+def get_num_transfer_tokens(text_masked_indices: torch.Tensor, text_steps: int) -> torch.Tensor:
+    """Same contract as the reference helper (:78-99): bool [B, T] -> int64 [B, text_steps]."""
+    counts = text_masked_indices.sum(dim=1).tolist()
+    return torch.tensor([_num_transfer_row(int(c), text_steps) for c in counts], dtype=torch.long,
+                        device=text_masked_indices.device)
+
+
+def add_gumbel_noise(logits, temperature=1.0, generator=None):  # pragma: no cover - fused into mmdp_text_step
+    raise NotImplementedError("fused into the text-step kernel (mmdp_text_step); see generate_ti2ti")
+
+
+def mask_by_random_topk(mask_len, probs, temperature=1.0, generator=None):  # pragma: no cover
+    raise NotImplementedError("fused into the image-step kernel (mmdp_image_step); see generate_ti2ti")
+
+
+class _Noise:
+    """Draws the reference's random tensors from the caller's generator (same calls, same order), on the generator's
+    device, and hands them to the kernels as device tensors."""
+
+    def __init__(self, generator: Optional[torch.Generator], device: torch.device):
+        self.g = generator
+        self.dev = device
+        self.gdev = generator.device if generator is not None else device
+
+    def _to(self, t):
+        return t if t.device == self.dev else t.to(self.dev, non_blocking=False)
+
+    def rand(self, shape):
+        return self._to(torch.rand(shape, dtype=torch.bfloat16, device=self.gdev, generator=self.g))
+
+    def exponential(self, shape):
+        return self._to(torch.empty(shape, dtype=torch.bfloat16, device=self.gdev).exponential_(1, generator=self.g))
+
+    def randn(self, shape):
+        return self._to(torch.randn(shape, dtype=torch.bfloat16, device=self.gdev, generator=self.g))
+
+
+@torch.no_grad()
+def generate_ti2ti(
+    model,
+    input_ids,
+    text_start,
+    text_end,
+    image_start,
+    seq_len,
+    newline_every,
+    text_steps=100,
+    text_gen_length=256,
+    text_block_length=64,
+    timesteps=100,
+    temperature=1.0,
+    text_temperature=0.7,
+    cfg_scale=0.0,
+    cfg_img=4.0,
+    uncon_text=None,
+    uncon_image=None,
+    tokenizer=None,
+    remasking="low_confidence",
+    noise_schedule=cosine_schedule,
+    generator=None,
+    text_vocab_size=126356,
+    codebook_size=8192,
+    _trace: Optional[list] = None,
+):
+    """Joint text+image mask-predict generation. Arguments, defaults, side effects (input_ids is not modified) and
+    return value `(List[int] image VQ tokens, str | List[int] text)` are those of the reference function."""
+    if remasking != "low_confidence":
+        # 'random' requests int64 uniform noise in the reference and raises there too (:195-197)
+        raise NotImplementedError(remasking)
+    if not hasattr(model, "forward_rows"):
+        raise TypeError("generate_ti2ti needs a mmada_parallel_b200.model.LLaDAForMultiModalGeneration (B200-native) model")
+    if input_ids.shape[0] != 1:
+        raise ValueError("the image path of generate_ti2ti is single-sample (reference :224/:340 read batch row 0 only)")
+    device = model.device
+    ids_host = input_ids.detach().to("cpu", torch.int64)
+    L = ids_host.shape[1]
+    ids = ids_host.to(device).clone().contiguous()                           # combined_input_ids (:140)
+
+    total_image_len = seq_len + seq_len // newline_every
+    image_end = image_start + total_image_len
+    print(f"Interleaved generation: {text_steps} total steps")
+    print(f"  - Text generation range: [{text_start}, {text_end})")
+    print(f"  - Image generation range: [{image_start}, {image_end}) (total {total_image_len} including newlines)")
+    print(f"  - VQ tokens: {seq_len}")
+
+    n_text = text_end - text_start
+    total_masks = int((ids_host[0, text_start:text_end] == MASK_TOKEN).sum())
+    num_transfer = _num_transfer_row(total_masks, text_steps)
+    img_steps = set(image_generation_step_indices(text_steps, timesteps))
+    pos_list = [i for i in range(image_start, image_end) if int(ids_host[0, i]) != NEW_LINE]
+    assert len(pos_list) == seq_len, f"Expected {seq_len} VQ tokens, got {len(pos_list)}"
+
+    text_rows = torch.arange(text_start, text_end, dtype=torch.int32, device=device)
+    pos = torch.tensor(pos_list, dtype=torch.int32, device=device)
+    use_uncond = (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None)
+    unc_t_ids = uncon_text.to(device=device, dtype=torch.int64) if uncon_text is not None else None
+    unc_i_ids = uncon_image.to(device=device, dtype=torch.int64) if uncon_image is not None else None
+
+    V = model.vocab_rows
+    text_logits = torch.empty((n_text, V), dtype=torch.bfloat16, device=device)
+    cond_vq = torch.empty((seq_len, codebook_size), dtype=torch.bfloat16, device=device)
+    unc_t_vq = torch.empty_like(cond_vq) if (use_uncond and cfg_scale != 0.0) else None
+    unc_i_vq = torch.empty_like(cond_vq) if (use_uncond and cfg_img != 0.0) else None
+    zeros_vq = None
+    x0_ws = torch.empty(n_text, dtype=torch.int64, device=device)
+    conf_ws = torch.empty(n_text, dtype=torch.float64, device=device)
+    sampled_ws = torch.empty(seq_len, dtype=torch.int32, device=device)
+    selp_ws = torch.empty(seq_len, dtype=torch.float32, device=device)
+    unk_ws = torch.empty(seq_len, dtype=torch.uint8, device=device)
+    scratch_ids = torch.empty_like(ids)
+    noise = _Noise(generator, device)
+    ids_text_ptr = ids.data_ptr() + text_start * 8
+
+    for step in range(text_steps):
+        is_img = step in img_steps
+        # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
+        model.forward_rows(ids, rows_a=text_rows, out_a=text_logits, rows_b=pos if is_img else None,
+                           col0_b=text_vocab_size, ncols_b=codebook_size, out_b=cond_vq if is_img else None)
+        # ---- text step (:181-217). A fully un-masked span makes the kernel a no-op, like the `.sum() > 0` guard.
+        un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
+        check(lib.mmdp_text_step(ptr(text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
+                                 ids_text_ptr, MASK_TOKEN, int(num_transfer[step]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+        if _trace is not None:
+            _trace.append({"step": step, "ids_after_text": ids[0].clone()})
+        if not is_img:
+            continue
+        # ---- image step (:220-344)
+        ua = ub = None
+        if use_uncond:
+            if cfg_scale != 0.0:
+                scratch_ids.copy_(ids)
+                if unc_t_ids is not None:
+                    scratch_ids[:, : unc_t_ids.shape[1]] = unc_t_ids
+                model.forward_rows(scratch_ids, rows_b=pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=unc_t_vq)
+                ua = unc_t_vq
+            if cfg_img != 0.0:
+                scratch_ids.copy_(ids)
+                if unc_i_ids is not None:
+                    scratch_ids[:, : unc_i_ids.shape[1]] = unc_i_ids
+                model.forward_rows(scratch_ids, rows_b=pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=unc_i_vq)
+                ub = unc_i_vq
+        elif cfg_scale != 0.0 or cfg_img != 0.0:
+            # no uncond inputs: the reference mixes against zeros (:277-278)
+            if zeros_vq is None:
+                zeros_vq = torch.zeros_like(cond_vq)
+            ua = zeros_vq if cfg_scale != 0.0 else None
+            ub = zeros_vq if cfg_img != 0.0 else None
+        q = noise.exponential((seq_len, codebook_size)) if temperature != 0 else None   # torch.multinomial's draw (:299-302)
+        ratio = 1.0 * (step + 1) / text_steps
+        img_temp = temperature * (1.0 - ratio)                                           # :330
+        rn = noise.randn((1, seq_len))                                                   # mask_by_random_topk (:30-31)
+        check(lib.mmdp_image_step(0, ptr(cond_vq), ptr(ua), ptr(ub), codebook_size, seq_len, codebook_size,
+                                  float(cfg_scale), float(cfg_img), ptr(q), ptr(rn), float(img_temp),
+                                  scheduled_mask_len(seq_len, step, text_steps, noise_schedule), ptr(ids), ptr(pos),
+                                  MASK_TOKEN, text_vocab_size, ptr(sampled_ws), ptr(selp_ws), ptr(unk_ws), None, None,
+                                  None, stream_ptr()))
+        if _trace is not None:
+            _trace[-1].update(sampled=sampled_ws.clone(), ids_after_image=ids[0].clone())
+
+    # ---- extract results (:346-368): the only device->host read of the call
+    final = ids[0].cpu()
+    text_tokens = [t for t in final[text_start:text_end].tolist() if t != MASK_TOKEN]
+    generated_text = tokenizer.decode(text_tokens, skip_special_tokens=True) if tokenizer is not None else text_tokens
+    image_tokens: List[int] = []
+    for t in final[torch.tensor(pos_list)].tolist():
+        if t != MASK_TOKEN:
+            image_tokens.append(max(0, min(t - text_vocab_size, codebook_size - 1)))
+        else:
+            # still masked -> sampled from the GLOBAL CPU RNG exactly like the reference (:362)
+            image_tokens.append(int(torch.randint(0, codebook_size, (1,)).item()))
+    print("Interleaved generation complete.")
+    print(f"  - Generated text: {len(text_tokens)} tokens")
+    print(f"  - Generated image: {len(image_tokens)} VQ tokens (range [0, {codebook_size}))")
+    return image_tokens, generated_text

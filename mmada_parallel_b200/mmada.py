@@ -1,0 +1,125 @@
+"""Drop-in for the variant-M model object: `MMadaModelLM.interleave_generate`
+(MMaDA-Parallel-M/models/modeling_mmada.py:118-248) on top of the same native forward.
+
+Differences from variant A that are preserved here:
+  * one forward per step over the CFG batch [cond; uncond] (B = 2), never B = 1 (:168-177);
+  * text logits are CFG-mixed: cond + text_cfg * (uncond - cond) (:179), argmax + fp64 softmax confidence on the mix;
+  * image logits are (1 + s) * cond - s * uncond (:216), ALWAYS sampled with torch.multinomial (:222);
+  * re-masking uses Gumbel noise and a strict `<` cut-off against the k-th smallest confidence (M/models/sampling.py:31-36);
+  * returns the sampled ids BEFORE re-masking and the text span, as tensors (:244-248).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .generators.parallel_generator import _Noise
+from .model import LLaDAForMultiModalGeneration
+from .schedule import cosine_schedule, get_num_transfer_tokens_m, image_generation_step_indices, scheduled_mask_len
+
+
+class MMadaModelLM(LLaDAForMultiModalGeneration):
+    def __init__(self, config, max_seq_len: Optional[int] = None, max_batch: int = 2, device: str = "cuda:0"):
+        super().__init__(config, max_seq_len=max_seq_len, max_batch=max(2, max_batch), device=device)
+
+    def forward(self, input_ids=None, **kw):
+        """M calls the backbone directly: `self(ids).logits` (modeling_mmada.py:172)."""
+        kw.pop("infer", None)
+        return super().forward(input_ids, infer=True, **kw)
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def interleave_generate(
+        self,
+        input_ids: torch.LongTensor = None,
+        uncond_input_ids: torch.LongTensor = None,
+        text_cfg: float = 0.0,
+        image_cfg: float = 3.5,
+        noise_schedule: Callable = cosine_schedule,
+        text_steps: int = 100,
+        image_steps: int = 100,
+        reserved_token_mapping: Dict = None,
+        generator: torch.Generator = None,
+        config=None,
+        remasking="low_confidence",
+        text_temperature: float = 0.0,
+        image_temperature: float = 1.0,
+        **kwargs,
+    ):
+        if not (text_cfg or image_cfg):
+            raise ValueError("text_cfg and image_cfg cannot be both 0")                      # :181-182
+        if remasking != "low_confidence":
+            raise NotImplementedError(remasking)
+        if text_temperature != 0:
+            raise NotImplementedError("M's text Gumbel path (fp64, global RNG, modeling_mmada.py:49-60) is not on the "
+                                      "B200 hot path; the reference default is text_temperature=0")
+        uni_prompting = kwargs.get("uni_prompting", None)
+        dev = self.device
+        mask_id = int(self.config.mask_token_id)
+        n_vq = int(config.model.mmada.num_vq_tokens)
+        C = int(config.model.mmada.codebook_size)
+        max_seq = int(config.dataset.preprocessing.max_seq_length)
+        tvoc = len(uni_prompting.text_tokenizer)
+        inp = input_ids.to(device=dev, dtype=torch.int64).unsqueeze(0)
+        unc = uncond_input_ids.to(device=dev, dtype=torch.int64).unsqueeze(0)
+        full = lambda n, v: torch.full((1, n), int(v), dtype=torch.int64, device=dev)
+        out_ids = torch.cat([full(1, reserved_token_mapping["<|soi|>"]), full(n_vq, mask_id),
+                             full(1, reserved_token_mapping["<|eoi|>"]), full(1, uni_prompting.text_tokenizer.bos_token_id),
+                             full(max_seq - 1, mask_id)], dim=1)                               # :142-148
+        P = inp.shape[1]
+        L = P + out_ids.shape[1]
+        if unc.shape[1] != P:
+            raise ValueError("cond and uncond prompts must have equal length (padding is not masked, SURVEY App. A3)")
+        both = torch.empty((2, L), dtype=torch.int64, device=dev)                             # [cond; uncond] id buffer
+        both[0, :P] = inp[0]
+        both[1, :P] = unc[0]
+        both[:, P:] = out_ids
+        num_transfer = get_num_transfer_tokens_m(max_seq - 1, text_steps)                     # bos is not a mask
+        img_idx = set(image_generation_step_indices(text_steps, image_steps))
+        V = self.vocab_rows
+        t0 = L - max_seq
+        rows_text = torch.cat([torch.arange(t0, L, dtype=torch.int32, device=dev),
+                               torch.arange(L + t0, 2 * L, dtype=torch.int32, device=dev)])
+        pos = torch.arange(P + 1, P + 1 + n_vq, dtype=torch.int32, device=dev)
+        rows_img = torch.cat([pos, pos + L])
+        text_logits = torch.empty((2 * max_seq, V), dtype=torch.bfloat16, device=dev)
+        img_logits = torch.empty((2 * n_vq, C), dtype=torch.bfloat16, device=dev)
+        x0_ws = torch.empty(max_seq, dtype=torch.int64, device=dev)
+        conf_ws = torch.empty(max_seq, dtype=torch.float64, device=dev)
+        sampled_ws = torch.zeros(n_vq, dtype=torch.int32, device=dev)
+        selp_ws = torch.empty(n_vq, dtype=torch.float32, device=dev)
+        unk_ws = torch.empty(n_vq, dtype=torch.uint8, device=dev)
+        noise = _Noise(generator, dev)
+        any_image_step = False
+        for i in range(text_steps):
+            is_img = i in img_idx
+            self.forward_rows(both, rows_a=rows_text, out_a=text_logits, rows_b=rows_img if is_img else None,
+                              col0_b=tvoc, ncols_b=C, out_b=img_logits if is_img else None)     # :172
+            # text step on the CFG-mixed logits (:179-209); only the cond row's ids change ...
+            check(lib.mmdp_text_step(ptr(text_logits), text_logits.data_ptr() + max_seq * V * 2, V, max_seq, V,
+                                     float(text_cfg), None, 0, 0.0, both.data_ptr() + t0 * 8, mask_id,
+                                     int(num_transfer[i]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+            # ... and the uncond row shares the generated suffix (:166-169)
+            both[1, P:] = both[0, P:]
+            if not is_img:
+                continue
+            any_image_step = True
+            q = noise.exponential((n_vq, C))                                                    # multinomial (:222)
+            ratio = 1.0 * (i + 1) / text_steps
+            temp = image_temperature * (1.0 - ratio)                                            # :236
+            # gumbel_noise(): torch.zeros_like(t).uniform_(0, 1, generator=generator)  (M/models/sampling.py:14-15)
+            un = torch.zeros((1, n_vq), dtype=torch.bfloat16, device=noise.gdev).uniform_(0, 1, generator=generator).to(dev)
+            check(lib.mmdp_image_step(1, ptr(img_logits), img_logits.data_ptr() + n_vq * C * 2, None, C, n_vq, C,
+                                      float(image_cfg), float(1 + image_cfg), ptr(q), ptr(un), float(temp),
+                                      scheduled_mask_len(n_vq, i, text_steps, noise_schedule), ptr(both), ptr(pos),
+                                      mask_id, tvoc, ptr(sampled_ws), ptr(selp_ws), ptr(unk_ws), None, None, None,
+                                      stream_ptr()))
+            both[1, P:] = both[0, P:]
+        if not any_image_step:
+            raise RuntimeError("no image step was scheduled (the reference would hit an undefined `sampled_ids`)")
+        return_image_ids = sampled_ws.to(torch.int64).unsqueeze(0)
+        return_text_ids = both[0:1, -max_seq:].clone()
+        return return_image_ids, return_text_ids

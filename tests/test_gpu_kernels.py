@@ -1,0 +1,145 @@
+"""tcgen05 GEMM / attention / norm kernels against fp32 torch references of the same op (floating-point kernels).
+Tolerances: the outputs are bf16 roundings of fp32-accumulated results; a different accumulation order may move a value
+across one rounding boundary, so the bound is 1 bf16 ulp of the result magnitude per bf16 rounding point on the path
+(2 for the residual epilogue, 3 for SwiGLU), stated per test."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def ref_linear(a, w):
+    return bf(a.float() @ w.float().t())
+
+
+def assert_ulp(got, want, ulps, what):
+    g, w = got.float(), want.float()
+    assert not torch.isnan(g).any(), what
+    scale = w.abs().max().clamp_min(1e-20)
+    # bf16 spacing at magnitude |w| is <= |w| * 2^-7; small entries are bounded by the spacing at 1/64 of the max
+    tol = ulps * torch.maximum(w.abs(), scale / 64) * 2.0 ** -7
+    bad = (g - w).abs() > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} outside {ulps} ulp; max abs err {float((g - w).abs().max())}"
+    assert (g != w).float().mean() < 0.02, f"{what}: too many roundings differ"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 8, 8), (333, 264, 200), (512, 1024, 1024), (2414, 4096, 512), (77, 8192, 256)])
+def test_gemm_plain(M, N, K):
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    w = bf(torch.randn(N, K, device="cuda") * 0.05)
+    assert_ulp(_lib.gemm_bf16(a, w), ref_linear(a, w), 1, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_strided_views():
+    """Row-strided A (lda > K) and a row window of W - the restricted LM head uses both."""
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(0)
+    abig = bf(torch.randn(300, 512, device="cuda"))
+    wbig = bf(torch.randn(2048, 256, device="cuda") * 0.05)
+    a = abig[:, 128:384]
+    w = wbig[520:520 + 264]
+    assert_ulp(_lib.gemm_bf16(a, w), ref_linear(a, w), 1, "strided gemm")
+
+
+def test_gemm_residual_and_inplace():
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(1)
+    a = bf(torch.randn(300, 768, device="cuda") * 0.5)
+    w = bf(torch.randn(512, 768, device="cuda") * 0.05)
+    r = bf(torch.randn(300, 512, device="cuda"))
+    want = bf(ref_linear(a, w).float() + r.float())
+    assert_ulp(_lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r), want, 2, "resid")
+    r2 = r.clone()
+    _lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r2, out=r2)
+    assert_ulp(r2, want, 2, "resid in place")
+
+
+def test_gemm_swiglu():
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(2)
+    M, K, ff = 300, 512, 512
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    w1 = bf(torch.randn(ff, K, device="cuda") * 0.08)
+    w3 = bf(torch.randn(ff, K, device="cuda") * 0.08)
+    wp = torch.empty(2 * ff, K, dtype=torch.bfloat16, device="cuda")
+    wp.view(ff // 128, 2, 128, K)[:, 0] = w1.view(ff // 128, 128, K)
+    wp.view(ff // 128, 2, 128, K)[:, 1] = w3.view(ff // 128, 128, K)
+    got = _lib.gemm_bf16(a, wp, _lib.EPI_SWIGLU)
+    want = bf(bf(torch.nn.functional.silu(ref_linear(a, w1).float())).float() * ref_linear(a, w3).float())
+    assert got.shape == (M, ff)
+    assert_ulp(got, want, 3, "swiglu")
+
+
+def test_gemm_rejects_bad_arguments():
+    from mmada_parallel_b200 import _lib
+    a = bf(torch.randn(16, 60, device="cuda"))  # K not a multiple of 8
+    w = bf(torch.randn(16, 60, device="cuda"))
+    with pytest.raises(_lib.MmdpError):
+        _lib.gemm_bf16(a, w)
+    with pytest.raises(_lib.MmdpError):
+        _lib.gemm_bf16(a.cpu(), w.cpu())  # no CPU fallback
+
+
+def ref_rope(t, cos, sin):
+    tf = t.float()
+    x1, x2 = tf[..., :64], tf[..., 64:]
+    c, s = cos[:, None, :], sin[:, None, :]
+    return bf(torch.cat([x1 * c + (-x2) * s, x2 * c + x1 * s], dim=-1))
+
+
+@pytest.mark.parametrize("B,L,H", [(1, 128, 2), (2, 200, 2), (1, 640, 4), (3, 77, 2), (1, 2414, 4)])
+def test_qkv_rope_and_attention(B, L, H):
+    from mmada_parallel_b200 import _lib
+    from mmada_parallel_b200.model import rope_tables
+    torch.manual_seed(B * 1000 + L + H)
+    d, M = H * 128, B * L
+    a = bf(torch.randn(M, d, device="cuda"))
+    wqkv = bf(torch.randn(3 * d, d, device="cuda") / math.sqrt(d))
+    cos, sin = (t.cuda() for t in rope_tables(128, 500000.0, L))
+    q, k, vt = _lib.qkv_rope(a, wqkv, H, L, cos, sin)
+    qkv = ref_linear(a, wqkv)
+    pos = torch.arange(M, device="cuda") % L
+    q_ref = ref_rope(qkv[:, :d].view(M, H, 128), cos[pos], sin[pos]).view(M, d)
+    k_ref = ref_rope(qkv[:, d:2 * d].view(M, H, 128), cos[pos], sin[pos]).view(M, d)
+    assert_ulp(q, q_ref, 2, "q rope")
+    assert_ulp(k, k_ref, 2, "k rope")
+    v_got = vt[..., :L].permute(0, 3, 1, 2).reshape(M, d)
+    assert_ulp(v_got, qkv[:, 2 * d:], 1, "v^T")
+    assert bool((vt[..., L:] == 0).all()), "pad columns of V^T must stay zero"
+    scale = 1.0 / math.sqrt(128.0)
+    o = _lib.attention(q, k, vt, B, H, L, scale)
+    qh = q.view(B, L, H, 128).transpose(1, 2).float()
+    kh = k.view(B, L, H, 128).transpose(1, 2).float()
+    vh = v_got.reshape(B, L, H, 128).transpose(1, 2).float()
+    o_ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1) @ vh).transpose(1, 2).reshape(M, d)
+    # P is rounded to bf16 before P.V (as in flash-style kernels): absolute error ~ 2^-8 * |v|_max * few
+    err = (o.float() - o_ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, vh.abs().max().item()), err
+    assert not torch.isnan(o.float()).any()
+
+
+def test_rmsnorm_embed_lfq():
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(3)
+    for M, d in [(300, 4096), (17, 256)]:
+        x = bf(torch.randn(M, d, device="cuda") * 3)
+        w = bf(1 + 0.1 * torch.randn(d, device="cuda"))
+        xf = x.float()
+        want = w * bf(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5))
+        assert_ulp(_lib.rmsnorm(x, w, 1e-5), want, 1, "rmsnorm")
+        rows = torch.tensor([3, 1, M - 1, 0], dtype=torch.int32, device="cuda")
+        assert_ulp(_lib.rmsnorm(x, w, 1e-5, rows=rows), want[rows.long()], 1, "rmsnorm rows")
+    wte = bf(torch.randn(1000, 256, device="cuda"))
+    ids = torch.randint(0, 1000, (77,), device="cuda")
+    assert torch.equal(_lib.embed(ids, wte), wte[ids])
+    vq = torch.randint(0, 8192, (2, 1024), device="cuda")
+    from oracle.sampling import lfq_codebook_entry
+    assert torch.equal(_lib.lfq_decode(vq, 13).cpu(), lfq_codebook_entry(vq.cpu(), 13))

@@ -1,0 +1,73 @@
+"""Host-side logic of the product package (no GPU): schedules, weight-name mapping, replica sharding (gloo, world 2)."""
+import os
+import socket
+import subprocess
+import sys
+
+import torch
+
+from helpers import ROOT
+from oracle import sampling as S
+
+
+def test_schedules_match_oracle():
+    from mmada_parallel_b200 import schedule as P
+    for n, steps in [(256, 128), (16, 8), (100, 7), (5, 9), (0, 4), (1, 1)]:
+        assert P.get_num_transfer_tokens(n, steps) == S.get_num_transfer_tokens_a(n, steps)
+        assert P.get_num_transfer_tokens_m(n, steps) == S.get_num_transfer_tokens_m(n, steps)
+    for ts, t in [(128, 64), (8, 4), (100, 100), (128, 128), (50, 30)]:
+        assert P.image_generation_step_indices(ts, t) == S.image_step_indices(ts, t)
+    assert [P.scheduled_mask_len(1024, s, 128) for s in range(128)] == [S.sched_len(1024, s, 128) for s in range(128)]
+    assert P.scheduled_mask_len(1024, 127, 128) == -1
+    m = torch.zeros(2, 10, dtype=torch.bool)
+    m[0, :7] = True
+    from mmada_parallel_b200.generators.parallel_generator import get_num_transfer_tokens
+    out = get_num_transfer_tokens(m, 4)
+    assert out.shape == (2, 4) and out[0].tolist() == S.get_num_transfer_tokens_a(7, 4) and out[1].tolist() == [0, 0, 0, 0]
+
+
+def test_weight_name_mapping():
+    from mmada_parallel_b200.model import LLaDAForMultiModalGeneration as M
+    f = M._native_name
+    assert f("model.transformer.wte.weight") == "wte"
+    assert f("model.transformer.ff_out.weight") == "head"
+    assert f("model.transformer.ln_f.weight") == "ln_f"
+    assert f("model.transformer.blocks.17.ff_out.weight") == "blocks.17.ff_out"
+    assert f("model.transformer.blocks.0.up_proj.weight") == "blocks.0.up_proj"
+    assert f("model.transformer.blocks.0.rotary_emb.inv_freq") is None
+    from oracle.llada import make_config, make_weights
+    cfg = make_config(vocab_size=1024, d_model=256)
+    names = {f(k) for k in make_weights(cfg, 0)}
+    assert None not in names and len(names) == 3 + 9 * cfg.n_layers
+
+
+def test_rope_table_matches_reference_formula():
+    from mmada_parallel_b200.model import rope_tables
+    from oracle.llada import rotary_tables
+    cos, sin = rope_tables(128, 500000.0, 300)
+    s, c = rotary_tables(128, 500000.0, 300)
+    assert torch.equal(cos, c[0, 0, :, :64]) and torch.equal(cos, c[0, 0, :, 64:])
+    assert torch.equal(sin, s[0, 0, :, :64]) and torch.equal(sin, s[0, 0, :, 64:])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_replica_sharding_gloo_world2():
+    """bench.py's multi-GPU mode = independent prompt replicas + a max-over-ranks time reduction; exercised here with
+    gloo on CPU (world_size 2): disjoint prompt shards that cover the job, and the reduction returns the slowest rank."""
+    port = _free_port()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_worker.py")],
+                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert "OK rank0 shard=[0, 2, 4] max_ms=20.0 total=5" in outs[0][0]
+    assert "OK rank1 shard=[1, 3] max_ms=20.0 total=5" in outs[1][0]
