@@ -34,6 +34,14 @@ extern "C" {
 MMDP_API int mmdp_version(void);
 MMDP_API const char* mmdp_last_error(void);
 
+/* ---- launch accounting (bench.py: gpu_launches and the live roofline pass) ------------------------------------------
+ * kinds: 0 = GEMM (work = flops), 1 = attention (flops), 2 = row kernels embed/rmsnorm/lfq (bytes), 3 = sampling (bytes).
+ * mmdp_prof_enable(1) brackets every subsequent launch with CUDA events on its stream; mmdp_prof_summary synchronises
+ * and returns, per kind, summed milliseconds / algorithmic work / launch count (arrays of 4). */
+MMDP_API void mmdp_prof_enable(int on);
+MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches);
+MMDP_API long long mmdp_launch_count(int reset);
+
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */
 #define MMDP_EPI_PLAIN 0   /* C = bf16(A W^T)                                 nn.Linear, modeling_llada.py:1402      */
 #define MMDP_EPI_RESID 1   /* C = bf16(bf16(A W^T) + R)                       attn_out :744 + :953; ff_out :968+:970  */

@@ -53,6 +53,9 @@ class ModelConfig(C.Structure):
 SIGNATURES = {
     "mmdp_version": (_i, []),
     "mmdp_last_error": (C.c_char_p, []),
+    "mmdp_prof_enable": (None, [_i]),
+    "mmdp_prof_summary": (_i, [_vp, _vp, _vp]),
+    "mmdp_launch_count": (C.c_longlong, [_i]),
     "mmdp_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "mmdp_qkv_rope": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdp_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
@@ -82,6 +85,13 @@ for _name, (_res, _args) in SIGNATURES.items():
 def check(rc: int) -> None:
     if rc != 0:
         raise MmdpError(lib.mmdp_last_error().decode("utf-8", "replace"))
+
+
+def prof_summary():
+    """{kind: (ms, work, launches)} accumulated since mmdp_prof_enable(1); synchronises the device."""
+    ms, work, n = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_longlong * 4)()
+    check(lib.mmdp_prof_summary(ms, work, n))
+    return {k: (ms[i], work[i], n[i]) for i, k in enumerate(("gemm", "attention", "row", "sampling"))}
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -28,6 +28,7 @@ int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream
     if (B <= 0 || N <= 0) return 0;
     if (bits <= 0 || bits > 62) return set_error("lfq_decode: bits out of range");
     dim3 grid((N + 255) / 256, B);
+    LaunchScope ls(LK_ROW, (double)B * N * (8 + 4.0 * bits), stream);
     lfq_kernel<<<grid, 256, 0, stream>>>(ids, zq, N, bits);
     MMDP_CUDA(cudaGetLastError());
     return 0;
@@ -132,6 +133,10 @@ MMDP_API int mmdp_image_remask(int variant, int N, const int32_t* sampled, const
 MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, void* stream) {
     return lfq_decode(ids, zq, B, N, bits, (cudaStream_t)stream);
 }
+
+MMDP_API void mmdp_prof_enable(int on) { prof_enable(on); }
+MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches) { return prof_summary(ms, work, launches); }
+MMDP_API long long mmdp_launch_count(int reset) { return launch_count(reset); }
 
 // ------------------------------------------------------------------------------------------------
 // model context
@@ -253,7 +258,7 @@ MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L,
     if (B <= 0 || B > c.max_batch || L <= 0 || L > c.max_seq_len)
         return set_error("mmdp_model_forward: B=%d L=%d outside workspace (max_batch=%d max_seq_len=%d)", B, L, c.max_batch, c.max_seq_len);
     if (L > m->rope_len) return set_error("mmdp_model_forward: rotary table covers %d positions, need %d", m->rope_len, L);
-    if (n_b > 0 && (col0_b < 0 || ncols_b <= 0 || col0_b + ncols_b > c.vocab_size || (ncols_b % 8) || (col0_b % 4)))
+    if (n_b > 0 && (col0_b < 0 || ncols_b <= 0 || col0_b + ncols_b > c.vocab_size || (ncols_b % 8)))
         return set_error("mmdp_model_forward: bad column window [%d,+%d)", col0_b, ncols_b);
     cudaStream_t s = (cudaStream_t)stream;
     const int d = c.d_model, ff = c.mlp_hidden, V = c.vocab_size, H = c.n_heads;

@@ -288,6 +288,7 @@ int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfl
     }
     dim3 grid((L + 127) / 128, H, B);
     const float scale_log2 = scale * 1.4426950408889634f;
+    LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)L * L * 128, stream);
     attention_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
     MMDP_CUDA(cudaGetLastError());
     return 0;

@@ -19,6 +19,7 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const __nv_bfloat1
 int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, int M, int d, int64_t vocab,
                cudaStream_t stream) {
     if (d % 8) return set_error("embed: d must be a multiple of 8");
+    LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read row + write row
     embed_kernel<<<M, 128, 0, stream>>>(ids, wte, x, d, vocab);
     MMDP_CUDA(cudaGetLastError());
     return 0;
@@ -76,6 +77,7 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
                  int M, int d, float eps, cudaStream_t stream) {
     if (M <= 0) return 0;
     if ((d % 8) || (ldx % 8) || (ldy % 8)) return set_error("rmsnorm: d/ldx/ldy must be multiples of 8");
+    LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read x + write y
     rmsnorm_kernel<<<M, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, d, eps);
     MMDP_CUDA(cudaGetLastError());
     return 0;

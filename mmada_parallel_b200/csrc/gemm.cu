@@ -296,6 +296,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
     gemm_bf16_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
     MMDP_CUDA(cudaGetLastError());
     return 0;

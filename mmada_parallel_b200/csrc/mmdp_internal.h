@@ -14,6 +14,19 @@ int set_error(const char* fmt, ...);  // records the message for mmdp_last_error
 const char* last_error();
 int num_sms();
 
+// Per-launch accounting. Every kernel launch of this library goes through a LaunchScope: it bumps the launch counter
+// and, when profiling is enabled (bench.py's roofline pass), brackets the launch with CUDA events on the launching stream.
+enum LaunchKind { LK_GEMM = 0, LK_ATTN = 1, LK_ROW = 2, LK_SAMPLE = 3, LK_COUNT = 4 };
+struct LaunchScope {
+    LaunchScope(int kind, double work, cudaStream_t s);
+    ~LaunchScope();
+    int idx;
+    cudaStream_t stream;
+};
+void prof_enable(int on);
+int prof_summary(double* ms, double* work, long long* launches);  // arrays of LK_COUNT; synchronises the device
+long long launch_count(int reset);
+
 #define MMDP_CUDA(expr)                                                                              \
     do {                                                                                             \
         cudaError_t _e = (expr);                                                                     \

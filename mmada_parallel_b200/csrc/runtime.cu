@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 namespace mmdp {
 
 static thread_local char g_err[1024] = "";
@@ -28,6 +30,53 @@ int num_sms() {
         n = prop.multiProcessorCount;
     }
     return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ------------------------------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t e0, e1; int kind; double work; };
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+static bool g_prof_on = false;
+static long long g_launches = 0;
+
+LaunchScope::LaunchScope(int kind, double work, cudaStream_t s) : idx(-1), stream(s) {
+    ++g_launches;
+    if (!g_prof_on) return;
+    if (g_prof_used == g_prof.size()) {
+        ProfRec r{};
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+        g_prof.push_back(r);
+    }
+    idx = (int)g_prof_used++;
+    g_prof[idx].kind = kind;
+    g_prof[idx].work = work;
+    cudaEventRecord(g_prof[idx].e0, s);
+}
+LaunchScope::~LaunchScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].e1, stream);
+}
+void prof_enable(int on) {
+    g_prof_on = on != 0;
+    g_prof_used = 0;
+}
+int prof_summary(double* ms, double* work, long long* launches) {
+    MMDP_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < LK_COUNT; ++k) { ms[k] = 0; work[k] = 0; launches[k] = 0; }
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        float t = 0.f;
+        MMDP_CUDA(cudaEventElapsedTime(&t, g_prof[i].e0, g_prof[i].e1));
+        ms[g_prof[i].kind] += t;
+        work[g_prof[i].kind] += g_prof[i].work;
+        launches[g_prof[i].kind] += 1;
+    }
+    return 0;
+}
+long long launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

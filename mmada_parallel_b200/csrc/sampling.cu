@@ -156,9 +156,13 @@ int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld
     if (R > 1024) return set_error("text_step: at most 1024 text positions");
     if ((V % 8) || (ld % 8) || (unoise && (ld_noise % 8))) return set_error("text_step: V/ld must be multiples of 8");
     TextRowArgs a{cond, uncond, unoise, ld, ld_noise, V, text_cfg, temperature, x0_ws, conf_ws};
-    text_rows_kernel<512><<<R, 512, 0, stream>>>(a);
+    {
+        LaunchScope ls(LK_SAMPLE, (double)R * V * 2 * (uncond ? 2 : 1) + (unoise ? (double)R * V * 2 : 0), stream);  // bytes read
+        text_rows_kernel<512><<<R, 512, 0, stream>>>(a);
+    }
     MMDP_CUDA(cudaGetLastError());
     const int threads = ((R + 31) / 32) * 32;
+    LaunchScope ls2(LK_SAMPLE, (double)R * 24, stream);
     text_commit_kernel<<<1, threads, R * sizeof(double), stream>>>(x0_ws, conf_ws, ids_text, R, mask_id, k);
     MMDP_CUDA(cudaGetLastError());
     return 0;
@@ -400,6 +404,7 @@ int image_remask(int variant, int N, const int32_t* sampled, const float* selp, 
     if (N <= 0 || N > 1024) return set_error("image_remask: N must be in [1, 1024]");
     RemaskArgs ma{N, variant, sampled, selp, unknown, conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
                   mask_len_out, masking_out};
+    LaunchScope ls(LK_SAMPLE, (double)N * 24, stream);
     image_remask_kernel<<<1, 1024, 0, stream>>>(ma);
     MMDP_CUDA(cudaGetLastError());
     return 0;
@@ -416,7 +421,11 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
     if (variant == 1 && !unc_a) return set_error("image_step: variant M needs uncond logits");
     ImageRowArgs ra{cond, unc_a, unc_b, ld, C, variant, s_a, s_b, qnoise, ids, pos, mask_id, vq_offset,
                     variant == 0 ? 1 : 0, sampled_ws, selp_ws, unknown_ws, probs_out};
-    image_rows_kernel<<<N, kImgThreads, 0, stream>>>(ra);
+    {
+        const int nt = 1 + (unc_a ? 1 : 0) + (unc_b ? 1 : 0) + (qnoise ? 1 : 0);
+        LaunchScope ls(LK_SAMPLE, (double)N * C * 2 * nt, stream);  // bytes read
+        image_rows_kernel<<<N, kImgThreads, 0, stream>>>(ra);
+    }
     MMDP_CUDA(cudaGetLastError());
     return image_remask(variant, N, sampled_ws, selp_ws, unknown_ws, conf_noise, temp, sched_len, ids, pos, mask_id,
                         vq_offset, mask_len_out, masking_out, stream);

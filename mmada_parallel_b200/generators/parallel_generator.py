@@ -67,6 +67,106 @@ class _Noise:
         return self._to(torch.randn(shape, dtype=torch.bfloat16, device=self.gdev, generator=self.g))
 
 
+class DenoiseState:
+    """Device-resident state of one generate_ti2ti call (ids, position maps, logits/workspace buffers)."""
+
+    def __init__(self, model, ids_host: torch.Tensor, text_start: int, text_end: int, image_start: int, seq_len: int,
+                 newline_every: int, uncon_text, uncon_image, cfg_scale: float, cfg_img: float, codebook_size: int):
+        device = model.device
+        self.model = model
+        self.L = ids_host.shape[1]
+        total_image_len = seq_len + seq_len // newline_every
+        image_end = image_start + total_image_len
+        self.text_start, self.text_end, self.seq_len = text_start, text_end, seq_len
+        self.n_text = text_end - text_start
+        self.total_masks = int((ids_host[0, text_start:text_end] == MASK_TOKEN).sum())
+        self.pos_list = [i for i in range(image_start, image_end) if int(ids_host[0, i]) != NEW_LINE]   # :164-167
+        assert len(self.pos_list) == seq_len, f"Expected {seq_len} VQ tokens, got {len(self.pos_list)}"
+        # one pinned staging buffer -> one H2D copy for everything the loop needs from the host
+        self.ids = ids_host.to(device, non_blocking=False).clone().contiguous()                       # combined_input_ids (:140)
+        self.text_rows = torch.arange(text_start, text_end, dtype=torch.int32, device=device)
+        self.pos = torch.tensor(self.pos_list, dtype=torch.int32, device=device)
+        self.use_uncond = (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None)
+        self.unc_t_ids = uncon_text.to(device=device, dtype=torch.int64) if uncon_text is not None else None
+        self.unc_i_ids = uncon_image.to(device=device, dtype=torch.int64) if uncon_image is not None else None
+        V = model.vocab_rows
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.text_logits = torch.empty((self.n_text, V), **bf)
+        self.cond_vq = torch.empty((seq_len, codebook_size), **bf)
+        self.unc_t_vq = torch.empty_like(self.cond_vq) if (self.use_uncond and cfg_scale != 0.0) else None
+        self.unc_i_vq = torch.empty_like(self.cond_vq) if (self.use_uncond and cfg_img != 0.0) else None
+        self.zeros_vq = torch.zeros_like(self.cond_vq) if (not self.use_uncond and (cfg_scale != 0.0 or cfg_img != 0.0)) else None
+        self.x0_ws = torch.empty(self.n_text, dtype=torch.int64, device=device)
+        self.conf_ws = torch.empty(self.n_text, dtype=torch.float64, device=device)
+        self.sampled_ws = torch.empty(seq_len, dtype=torch.int32, device=device)
+        self.selp_ws = torch.empty(seq_len, dtype=torch.float32, device=device)
+        self.unk_ws = torch.empty(seq_len, dtype=torch.uint8, device=device)
+        self.scratch_ids = torch.empty_like(self.ids)
+
+    def bytes_h2d(self) -> int:
+        n = self.ids.numel() * 8
+        n += self.unc_t_ids.numel() * 8 if self.unc_t_ids is not None else 0
+        n += self.unc_i_ids.numel() * 8 if self.unc_i_ids is not None else 0
+        return n
+
+
+def denoise_loop(st: DenoiseState, text_steps: int, timesteps: int, temperature: float, text_temperature: float,
+                 cfg_scale: float, cfg_img: float, noise_schedule, generator, text_vocab_size: int, codebook_size: int,
+                 _trace: Optional[list] = None) -> torch.Tensor:
+    """The hot loop (parallel_generator.py:174-344) on device-resident state; returns the id buffer (device).
+    No host<->device synchronisation happens in here."""
+    model, ids, V, n_text, seq_len = st.model, st.ids, st.model.vocab_rows, st.n_text, st.seq_len
+    num_transfer = _num_transfer_row(st.total_masks, text_steps)                              # :153-154
+    img_steps = set(image_generation_step_indices(text_steps, timesteps))                     # :157-159
+    noise = _Noise(generator, model.device)
+    ids_text_ptr = ids.data_ptr() + st.text_start * 8
+    for step in range(text_steps):
+        is_img = step in img_steps
+        # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
+        model.forward_rows(ids, rows_a=st.text_rows, out_a=st.text_logits, rows_b=st.pos if is_img else None,
+                           col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.cond_vq if is_img else None)
+        # ---- text step (:181-217). A fully un-masked span makes the kernel a no-op, like the `.sum() > 0` guard.
+        un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
+        check(lib.mmdp_text_step(ptr(st.text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
+                                 ids_text_ptr, MASK_TOKEN, int(num_transfer[step]), ptr(st.x0_ws), ptr(st.conf_ws),
+                                 stream_ptr()))
+        if _trace is not None:
+            _trace.append({"step": step, "ids_after_text": ids[0].clone()})
+        if not is_img:
+            continue
+        # ---- image step (:220-344)
+        ua = ub = None
+        if st.use_uncond:
+            if cfg_scale != 0.0:
+                st.scratch_ids.copy_(ids)
+                if st.unc_t_ids is not None:
+                    st.scratch_ids[:, : st.unc_t_ids.shape[1]] = st.unc_t_ids
+                model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_t_vq)
+                ua = st.unc_t_vq
+            if cfg_img != 0.0:
+                st.scratch_ids.copy_(ids)
+                if st.unc_i_ids is not None:
+                    st.scratch_ids[:, : st.unc_i_ids.shape[1]] = st.unc_i_ids
+                model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_i_vq)
+                ub = st.unc_i_vq
+        elif st.zeros_vq is not None:
+            # no uncond inputs: the reference mixes against zeros (:277-278)
+            ua = st.zeros_vq if cfg_scale != 0.0 else None
+            ub = st.zeros_vq if cfg_img != 0.0 else None
+        q = noise.exponential((seq_len, codebook_size)) if temperature != 0 else None   # torch.multinomial's draw (:299-302)
+        ratio = 1.0 * (step + 1) / text_steps
+        img_temp = temperature * (1.0 - ratio)                                           # :330
+        rn = noise.randn((1, seq_len))                                                   # mask_by_random_topk (:30-31)
+        check(lib.mmdp_image_step(0, ptr(st.cond_vq), ptr(ua), ptr(ub), codebook_size, seq_len, codebook_size,
+                                  float(cfg_scale), float(cfg_img), ptr(q), ptr(rn), float(img_temp),
+                                  scheduled_mask_len(seq_len, step, text_steps, noise_schedule), ptr(ids), ptr(st.pos),
+                                  MASK_TOKEN, text_vocab_size, ptr(st.sampled_ws), ptr(st.selp_ws), ptr(st.unk_ws), None,
+                                  None, None, stream_ptr()))
+        if _trace is not None:
+            _trace[-1].update(sampled=st.sampled_ws.clone(), ids_after_image=ids[0].clone())
+    return ids
+
+
 @torch.no_grad()
 def generate_ti2ti(
     model,
@@ -103,98 +203,23 @@ def generate_ti2ti(
         raise TypeError("generate_ti2ti needs a mmada_parallel_b200.model.LLaDAForMultiModalGeneration (B200-native) model")
     if input_ids.shape[0] != 1:
         raise ValueError("the image path of generate_ti2ti is single-sample (reference :224/:340 read batch row 0 only)")
-    device = model.device
     ids_host = input_ids.detach().to("cpu", torch.int64)
-    L = ids_host.shape[1]
-    ids = ids_host.to(device).clone().contiguous()                           # combined_input_ids (:140)
-
     total_image_len = seq_len + seq_len // newline_every
-    image_end = image_start + total_image_len
     print(f"Interleaved generation: {text_steps} total steps")
     print(f"  - Text generation range: [{text_start}, {text_end})")
-    print(f"  - Image generation range: [{image_start}, {image_end}) (total {total_image_len} including newlines)")
+    print(f"  - Image generation range: [{image_start}, {image_start + total_image_len}) (total {total_image_len} including newlines)")
     print(f"  - VQ tokens: {seq_len}")
-
-    n_text = text_end - text_start
-    total_masks = int((ids_host[0, text_start:text_end] == MASK_TOKEN).sum())
-    num_transfer = _num_transfer_row(total_masks, text_steps)
-    img_steps = set(image_generation_step_indices(text_steps, timesteps))
-    pos_list = [i for i in range(image_start, image_end) if int(ids_host[0, i]) != NEW_LINE]
-    assert len(pos_list) == seq_len, f"Expected {seq_len} VQ tokens, got {len(pos_list)}"
-
-    text_rows = torch.arange(text_start, text_end, dtype=torch.int32, device=device)
-    pos = torch.tensor(pos_list, dtype=torch.int32, device=device)
-    use_uncond = (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None)
-    unc_t_ids = uncon_text.to(device=device, dtype=torch.int64) if uncon_text is not None else None
-    unc_i_ids = uncon_image.to(device=device, dtype=torch.int64) if uncon_image is not None else None
-
-    V = model.vocab_rows
-    text_logits = torch.empty((n_text, V), dtype=torch.bfloat16, device=device)
-    cond_vq = torch.empty((seq_len, codebook_size), dtype=torch.bfloat16, device=device)
-    unc_t_vq = torch.empty_like(cond_vq) if (use_uncond and cfg_scale != 0.0) else None
-    unc_i_vq = torch.empty_like(cond_vq) if (use_uncond and cfg_img != 0.0) else None
-    zeros_vq = None
-    x0_ws = torch.empty(n_text, dtype=torch.int64, device=device)
-    conf_ws = torch.empty(n_text, dtype=torch.float64, device=device)
-    sampled_ws = torch.empty(seq_len, dtype=torch.int32, device=device)
-    selp_ws = torch.empty(seq_len, dtype=torch.float32, device=device)
-    unk_ws = torch.empty(seq_len, dtype=torch.uint8, device=device)
-    scratch_ids = torch.empty_like(ids)
-    noise = _Noise(generator, device)
-    ids_text_ptr = ids.data_ptr() + text_start * 8
-
-    for step in range(text_steps):
-        is_img = step in img_steps
-        # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
-        model.forward_rows(ids, rows_a=text_rows, out_a=text_logits, rows_b=pos if is_img else None,
-                           col0_b=text_vocab_size, ncols_b=codebook_size, out_b=cond_vq if is_img else None)
-        # ---- text step (:181-217). A fully un-masked span makes the kernel a no-op, like the `.sum() > 0` guard.
-        un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
-        check(lib.mmdp_text_step(ptr(text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
-                                 ids_text_ptr, MASK_TOKEN, int(num_transfer[step]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
-        if _trace is not None:
-            _trace.append({"step": step, "ids_after_text": ids[0].clone()})
-        if not is_img:
-            continue
-        # ---- image step (:220-344)
-        ua = ub = None
-        if use_uncond:
-            if cfg_scale != 0.0:
-                scratch_ids.copy_(ids)
-                if unc_t_ids is not None:
-                    scratch_ids[:, : unc_t_ids.shape[1]] = unc_t_ids
-                model.forward_rows(scratch_ids, rows_b=pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=unc_t_vq)
-                ua = unc_t_vq
-            if cfg_img != 0.0:
-                scratch_ids.copy_(ids)
-                if unc_i_ids is not None:
-                    scratch_ids[:, : unc_i_ids.shape[1]] = unc_i_ids
-                model.forward_rows(scratch_ids, rows_b=pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=unc_i_vq)
-                ub = unc_i_vq
-        elif cfg_scale != 0.0 or cfg_img != 0.0:
-            # no uncond inputs: the reference mixes against zeros (:277-278)
-            if zeros_vq is None:
-                zeros_vq = torch.zeros_like(cond_vq)
-            ua = zeros_vq if cfg_scale != 0.0 else None
-            ub = zeros_vq if cfg_img != 0.0 else None
-        q = noise.exponential((seq_len, codebook_size)) if temperature != 0 else None   # torch.multinomial's draw (:299-302)
-        ratio = 1.0 * (step + 1) / text_steps
-        img_temp = temperature * (1.0 - ratio)                                           # :330
-        rn = noise.randn((1, seq_len))                                                   # mask_by_random_topk (:30-31)
-        check(lib.mmdp_image_step(0, ptr(cond_vq), ptr(ua), ptr(ub), codebook_size, seq_len, codebook_size,
-                                  float(cfg_scale), float(cfg_img), ptr(q), ptr(rn), float(img_temp),
-                                  scheduled_mask_len(seq_len, step, text_steps, noise_schedule), ptr(ids), ptr(pos),
-                                  MASK_TOKEN, text_vocab_size, ptr(sampled_ws), ptr(selp_ws), ptr(unk_ws), None, None,
-                                  None, stream_ptr()))
-        if _trace is not None:
-            _trace[-1].update(sampled=sampled_ws.clone(), ids_after_image=ids[0].clone())
+    st = DenoiseState(model, ids_host, text_start, text_end, image_start, seq_len, newline_every, uncon_text, uncon_image,
+                      cfg_scale, cfg_img, codebook_size)
+    ids = denoise_loop(st, text_steps, timesteps, temperature, text_temperature, cfg_scale, cfg_img, noise_schedule,
+                       generator, text_vocab_size, codebook_size, _trace)
 
     # ---- extract results (:346-368): the only device->host read of the call
     final = ids[0].cpu()
     text_tokens = [t for t in final[text_start:text_end].tolist() if t != MASK_TOKEN]
     generated_text = tokenizer.decode(text_tokens, skip_special_tokens=True) if tokenizer is not None else text_tokens
     image_tokens: List[int] = []
-    for t in final[torch.tensor(pos_list)].tolist():
+    for t in final[torch.tensor(st.pos_list)].tolist():
         if t != MASK_TOKEN:
             image_tokens.append(max(0, min(t - text_vocab_size, codebook_size - 1)))
         else:

@@ -18,12 +18,15 @@ def ref_linear(a, w):
     return bf(a.float() @ w.float().t())
 
 
-def assert_ulp(got, want, ulps, what):
+def assert_ulp(got, want, ulps, what, mag=None):
+    """|got - want| <= ulps * (bf16 spacing at the magnitude of the quantities that were rounded). `mag` carries the
+    magnitude of the operands when the result is a sum that can cancel (residual add, rotary)."""
     g, w = got.float(), want.float()
     assert not torch.isnan(g).any(), what
     scale = w.abs().max().clamp_min(1e-20)
-    # bf16 spacing at magnitude |w| is <= |w| * 2^-7; small entries are bounded by the spacing at 1/64 of the max
-    tol = ulps * torch.maximum(w.abs(), scale / 64) * 2.0 ** -7
+    ref_mag = w.abs() if mag is None else torch.maximum(w.abs(), mag.float().abs())
+    # bf16 spacing at magnitude m is <= m * 2^-7; tiny entries are bounded by the spacing at 1/64 of the max
+    tol = ulps * torch.maximum(ref_mag, scale / 64) * 2.0 ** -7
     bad = (g - w).abs() > tol
     assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} outside {ulps} ulp; max abs err {float((g - w).abs().max())}"
     assert (g != w).float().mean() < 0.02, f"{what}: too many roundings differ"
@@ -55,11 +58,12 @@ def test_gemm_residual_and_inplace():
     a = bf(torch.randn(300, 768, device="cuda") * 0.5)
     w = bf(torch.randn(512, 768, device="cuda") * 0.05)
     r = bf(torch.randn(300, 512, device="cuda"))
-    want = bf(ref_linear(a, w).float() + r.float())
-    assert_ulp(_lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r), want, 2, "resid")
+    lin = ref_linear(a, w)
+    want = bf(lin.float() + r.float())
+    assert_ulp(_lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r), want, 2, "resid", mag=lin)
     r2 = r.clone()
     _lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r2, out=r2)
-    assert_ulp(r2, want, 2, "resid in place")
+    assert_ulp(r2, want, 2, "resid in place", mag=lin)
 
 
 def test_gemm_swiglu():
@@ -109,8 +113,11 @@ def test_qkv_rope_and_attention(B, L, H):
     pos = torch.arange(M, device="cuda") % L
     q_ref = ref_rope(qkv[:, :d].view(M, H, 128), cos[pos], sin[pos]).view(M, d)
     k_ref = ref_rope(qkv[:, d:2 * d].view(M, H, 128), cos[pos], sin[pos]).view(M, d)
-    assert_ulp(q, q_ref, 2, "q rope")
-    assert_ulp(k, k_ref, 2, "k rope")
+    def pair_mag(x):  # rotary mixes element i with i +- 64 of the same head: both magnitudes bound the rounding error
+        xh = x.view(M, H, 2, 64).float().abs()
+        return torch.maximum(xh[:, :, 0], xh[:, :, 1]).repeat(1, 1, 2).view(M, d)
+    assert_ulp(q, q_ref, 2, "q rope", mag=pair_mag(qkv[:, :d]))
+    assert_ulp(k, k_ref, 2, "k rope", mag=pair_mag(qkv[:, d:2 * d]))
     v_got = vt[..., :L].permute(0, 3, 1, 2).reshape(M, d)
     assert_ulp(v_got, qkv[:, 2 * d:], 1, "v^T")
     assert bool((vt[..., L:] == 0).all()), "pad columns of V^T must stay zero"

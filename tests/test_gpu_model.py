@@ -113,7 +113,7 @@ def test_generate_errors_match_reference():
     a = _args(lay)
     with pytest.raises(NotImplementedError):
         generate_ti2ti(model, lay["input_ids"], remasking="bogus", **a)
-    bad = dict(a, seq_len=a["seq_len"] + 1)
+    bad = dict(a, newline_every=3)  # position map no longer yields seq_len VQ slots -> reference assertion (:169)
     with pytest.raises(AssertionError), quiet():
         generate_ti2ti(model, lay["input_ids"], text_steps=2, timesteps=1, **bad)
 
