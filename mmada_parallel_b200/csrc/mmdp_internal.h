@@ -38,6 +38,20 @@ long long launch_count(int reset);
 // 128-byte swizzle (box_cols must be 64), out-of-bounds elements read as zero.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                       uint32_t box_cols);
+// generic: elem_bytes 2 (bf16, box_cols 64) or 4 (fp32/tf32, box_cols 32)
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols);
+
+// TF32 shifted-tap GEMM (conv engine) and the decoder's row kernels (conv_tf32.cu)
+int conv_tf32(const float* A, int lda, long long a_rows, const float* W, int M, int N, int K, int T, const int* shifts,
+              float* C, int ldc, const float* R, int ldr, const float* bias, int bias_along_m, float alpha, int pad_w,
+              int pad_h, int scatter_w, int scatter_h, cudaStream_t stream);
+int gn_swish(const float* x, float* y, int B, int C, int H, int W, double* stats_ws, const float* gamma, const float* beta,
+             float eps, int swish, int compact, cudaStream_t stream);
+int upsample2x(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
+int softmax_rows(float* s, int rows, int n, cudaStream_t stream);
+int lfq_to_padded(const int64_t* ids, float* z, int B, int H, int W, int bits, int Cpad, cudaStream_t stream);
+int padded_to_nchw(const float* x, float* y, int B, int C, int ld, int H, int W, cudaStream_t stream);
 
 struct QkvRopeArgs {
     __nv_bfloat16* q;       // [B*L, d_model]   rotary applied, head h at columns [128h, 128h+128)

@@ -98,15 +98,21 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                       uint32_t box_cols) {
+    return make_tmap_2d(out, base, 2, rows, cols, ld, box_rows, box_cols);
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error("cuTensorMapEncodeTiled not available (no CUDA driver / no GPU)");
-    if (box_cols != 64) return set_error("tmap: box_cols must be 64 (one 128-byte swizzle atom)");
+    if (elem_bytes != 2 && elem_bytes != 4) return set_error("tmap: element size must be 2 (bf16) or 4 (fp32)");
+    if (box_cols * (uint32_t)elem_bytes != 128) return set_error("tmap: box must be exactly one 128-byte swizzle atom wide");
     if (box_rows == 0 || box_rows > 256) return set_error("tmap: box_rows out of range");
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {ld * 2};
+    cuuint64_t gstride[1] = {ld * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)

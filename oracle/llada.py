@@ -113,6 +113,7 @@ def forward_hidden(ids: torch.Tensor, w: Dict[str, torch.Tensor], cfg) -> torch.
     B, T = ids.shape
     x = F.embedding(ids, w["model.transformer.wte.weight"])
     pos_sin, pos_cos = rotary_tables(cfg.d_model // cfg.n_heads, cfg.rope_theta, T)
+    pos_sin, pos_cos = pos_sin.to(x.device), pos_cos.to(x.device)  # (tables are built on the CPU like the checker's)
     for i in range(cfg.n_layers):
         x = block_forward(x, w, f"model.transformer.blocks.{i}.", cfg, pos_sin, pos_cos)
     return rms_norm(x, w["model.transformer.ln_f.weight"], cfg.rms_norm_eps)
