@@ -110,6 +110,29 @@ MMDP_API int mmdp_image_remask(int variant, int N, const int32_t* sampled, const
 /* LFQuantizer.get_codebook_entry (modeling_magvitv2.py:208-221): ids [B, N] -> z_q fp32 [B, bits, N] (+-1). */
 MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, void* stream);
 
+/* ---- VQ decoder context: MAGVITv2.decode_code (M/models/modeling_magvitv2.py:429-433, VQGANDecoder :278-399) -------- */
+typedef struct mmdp_vqdec mmdp_vqdec;
+typedef struct {
+    int32_t ch;                 /* 128 */
+    int32_t n_levels;           /* len(ch_mult), <= 8 */
+    int32_t ch_mult[8];         /* (1, 1, 2, 2, 4) */
+    int32_t num_res_blocks[8];  /* (4, 4, 3, 4, 3) */
+    int32_t z_channels;         /* 13 = LFQ bits */
+    int32_t out_ch;             /* 3 */
+    int32_t max_batch;
+    int32_t latent_h, latent_w; /* 32 x 32 code grid -> 512 x 512 pixels */
+} mmdp_vqdec_config;
+
+MMDP_API int mmdp_vqdec_create(const mmdp_vqdec_config* cfg, mmdp_vqdec** out);
+MMDP_API void mmdp_vqdec_destroy(mmdp_vqdec* d);
+/* name = reference parameter name ("decoder.conv_in.weight", "decoder.up.3.block.0.norm1.bias", ...); src = fp32, device or
+ * host pointer, reference layout (conv: OIHW). Convolution weights are repacked to the tap-major layout of the TF32 GEMM. */
+MMDP_API int mmdp_vqdec_set_weight(mmdp_vqdec* d, const char* name, const float* src, int64_t numel, void* stream);
+/* number of parameters not loaded yet (names written space-separated into out, truncated to out_len) */
+MMDP_API int mmdp_vqdec_missing(mmdp_vqdec* d, char* out, int out_len);
+/* ids int64 [B, h*w] (device) -> pixels fp32 [B, out_ch, H, W] (device), H = h * 2^(n_levels-1). */
+MMDP_API int mmdp_vqdec_decode(mmdp_vqdec* d, const int64_t* ids, int B, int h, int w, float* out_nchw, void* stream);
+
 /* ---- whole-model context (LLaDAModel.forward, modeling_llada.py:1201-1415) ----------------------------------- */
 typedef struct mmdp_model mmdp_model;
 

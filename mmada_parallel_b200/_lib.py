@@ -36,6 +36,12 @@ lib = _load()
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 
+class VqDecConfig(C.Structure):
+    _fields_ = [("ch", C.c_int32), ("n_levels", C.c_int32), ("ch_mult", C.c_int32 * 8), ("num_res_blocks", C.c_int32 * 8),
+                ("z_channels", C.c_int32), ("out_ch", C.c_int32), ("max_batch", C.c_int32), ("latent_h", C.c_int32),
+                ("latent_w", C.c_int32)]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [
         ("d_model", C.c_int32),
@@ -68,6 +74,11 @@ SIGNATURES = {
     ),
     "mmdp_image_remask": (_i, [_i, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "mmdp_lfq_decode": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mmdp_vqdec_create": (_i, [C.POINTER(VqDecConfig), C.POINTER(_vp)]),
+    "mmdp_vqdec_destroy": (None, [_vp]),
+    "mmdp_vqdec_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "mmdp_vqdec_missing": (_i, [_vp, C.c_char_p, _i]),
+    "mmdp_vqdec_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "mmdp_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "mmdp_model_destroy": (None, [_vp]),
     "mmdp_model_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i64, _vp]),

@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
 }
 
 // in-place row softmax of an fp32 matrix [rows, n]
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, int n) {
-    float* row = s + (size_t)blockIdx.x * n;
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, int n, int ld) {
+    float* row = s + (size_t)blockIdx.x * ld;
     __shared__ float red[8];
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, row[i]);
@@ -373,9 +373,31 @@ int upsample2x(const float* x, float* y, int B, int C, int H, int W, cudaStream_
     return 0;
 }
 
-int softmax_rows(float* s, int rows, int n, cudaStream_t stream) {
+int softmax_rows_ld(float* s, int rows, int n, int ld, cudaStream_t stream) {
     LaunchScope ls(LK_ROW, (double)rows * n * 8, stream);
-    softmax_rows_kernel<<<rows, 256, 0, stream>>>(s, n);
+    softmax_rows_kernel<<<rows, 256, 0, stream>>>(s, n, ld);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// zero the one-pixel border of padded NHWC images
+__global__ void zero_border_kernel(float* __restrict__ y, int C, int H, int W) {
+    const int b = blockIdx.y, Wp = W + 2, Hp = H + 2;
+    const int nb = 2 * Wp + 2 * H;  // border pixels per image
+    const long long n = (long long)nb * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int j = (int)(i / C);
+        int yy, xx;
+        if (j < Wp) { yy = 0; xx = j; }
+        else if (j < 2 * Wp) { yy = Hp - 1; xx = j - Wp; }
+        else { const int r = j - 2 * Wp; yy = 1 + r / 2; xx = (r & 1) ? Wp - 1 : 0; }
+        y[((size_t)b * Hp * Wp + (size_t)yy * Wp + xx) * C + c] = 0.f;
+    }
+}
+int zero_border(float* y, int B, int C, int H, int W, cudaStream_t stream) {
+    LaunchScope ls(LK_ROW, (double)B * (2 * (W + 2) + 2 * H) * C * 4, stream);
+    zero_border_kernel<<<dim3(64, B), 256, 0, stream>>>(y, C, H, W);
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }

@@ -49,7 +49,8 @@ int conv_tf32(const float* A, int lda, long long a_rows, const float* W, int M, 
 int gn_swish(const float* x, float* y, int B, int C, int H, int W, double* stats_ws, const float* gamma, const float* beta,
              float eps, int swish, int compact, cudaStream_t stream);
 int upsample2x(const float* x, float* y, int B, int C, int H, int W, cudaStream_t stream);
-int softmax_rows(float* s, int rows, int n, cudaStream_t stream);
+int softmax_rows_ld(float* s, int rows, int n, int ld, cudaStream_t stream);
+int zero_border(float* y, int B, int C, int H, int W, cudaStream_t stream);
 int lfq_to_padded(const int64_t* ids, float* z, int B, int H, int W, int bits, int Cpad, cudaStream_t stream);
 int padded_to_nchw(const float* x, float* y, int B, int C, int ld, int H, int W, cudaStream_t stream);
 

@@ -1,0 +1,96 @@
+"""Drop-in for the decode side of MMaDA-Parallel-M/models/modeling_magvitv2.py: `MAGVITv2.decode_code`
+(:429-433) = LFQuantizer.get_codebook_entry (:208-221) + VQGANDecoder.forward (:365-399), as one C call into the native
+decoder context (TF32 tcgen05 implicit-GEMM convolutions, csrc/conv_tf32.cu + csrc/vq_decoder.cu).
+
+Numerics: the reference module runs in fp32; on a GPU its convolutions go through cuDNN with TF32 allowed (PyTorch
+default), which is the precision of this implementation (10-bit mantissa products, fp32 accumulation). Tolerance against
+the fp32 CPU oracle is stated in tests/test_gpu_magvit.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Dict, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+
+class VQGANDecoder:
+    def __init__(self, ch: int = 128, ch_mult: Sequence[int] = (1, 1, 2, 2, 4), num_res_blocks: Sequence[int] = (4, 4, 3, 4, 3),
+                 z_channels: int = 13, out_ch: int = 3, latent_hw=(32, 32), max_batch: int = 1, device: str = "cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.MmdpError("mmada_parallel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.cfg = SimpleNamespace(ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=tuple(num_res_blocks), z_channels=z_channels,
+                                   out_ch=out_ch, latent_hw=tuple(latent_hw), max_batch=max_batch)
+        c = _lib.VqDecConfig()
+        c.ch, c.n_levels, c.z_channels, c.out_ch, c.max_batch = ch, len(ch_mult), z_channels, out_ch, max_batch
+        c.latent_h, c.latent_w = latent_hw
+        for i, (m, n) in enumerate(zip(ch_mult, num_res_blocks)):
+            c.ch_mult[i], c.num_res_blocks[i] = m, n
+        h = C.c_void_p()
+        check(lib.mmdp_vqdec_create(C.byref(c), C.byref(h)))
+        self._h = h
+        self.upscale = 2 ** (len(ch_mult) - 1)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            lib.mmdp_vqdec_destroy(h)
+            self._h = None
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], prefix: str = "decoder.", strict: bool = True):
+        """Accepts the reference module's names, with the 'decoder.' prefix (MAGVITv2 state dict) or without it."""
+        unexpected = []
+        for k, v in state_dict.items():
+            if k.startswith("encoder.") or k.startswith("quantize."):
+                continue
+            name = k if k.startswith("decoder.") else prefix + k
+            t = v.detach().to(torch.float32).contiguous()
+            rc = lib.mmdp_vqdec_set_weight(self._h, name.encode(), t.data_ptr(), t.numel(), stream_ptr())
+            if rc != 0:
+                unexpected.append(k)
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(512)
+        missing = lib.mmdp_vqdec_missing(self._h, buf, 512)
+        if strict and (missing or unexpected):
+            raise KeyError(f"VQGANDecoder.load_state_dict: {missing} missing ({buf.value.decode()[:200]}), unexpected={unexpected[:6]}")
+        return SimpleNamespace(missing_keys=buf.value.decode().split(), unexpected_keys=unexpected)
+
+    def decode_ids(self, ids: torch.Tensor, shape=None) -> torch.Tensor:
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        b, n = ids.shape
+        h, w = shape if shape is not None else (int(n ** 0.5), int(n ** 0.5))
+        if h * w != n:
+            raise ValueError(f"decode_code: {n} indices do not form a {h}x{w} grid")
+        out = torch.empty((b, self.cfg.out_ch, h * self.upscale, w * self.upscale), dtype=torch.float32, device=self.device)
+        check(lib.mmdp_vqdec_decode(self._h, ptr(ids), b, h, w, ptr(out), stream_ptr()))
+        return out
+
+
+class MAGVITv2:
+    """Inference-side mirror of the reference class: `decode_code(ids[B, N], shape=None) -> FloatTensor[B, 3, H, W]`."""
+
+    def __init__(self, max_batch: int = 1, device: str = "cuda:0", **decoder_kw):
+        self.decoder = VQGANDecoder(max_batch=max_batch, device=device, **decoder_kw)
+        self.device = self.decoder.device
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        return self.decoder.load_state_dict(state_dict, strict=strict)
+
+    def eval(self):
+        return self
+
+    def to(self, *_a, **_k):
+        return self
+
+    @torch.no_grad()
+    def decode_code(self, codebook_indices: torch.Tensor, shape=None) -> torch.Tensor:
+        return self.decoder.decode_ids(codebook_indices, shape=shape)
+
+    def get_code(self, pixel_values):
+        raise NotImplementedError("VQ encode (MAGVITv2.get_code, :423-427) is the next row of the scope table (SURVEY.md 8f rank 1)")

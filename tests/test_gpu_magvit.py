@@ -1,0 +1,52 @@
+"""MAGVITv2.decode_code on the B200 (TF32 tcgen05 convolutions) against the golden images produced by the REAL
+reference decoder (fp32, CPU; oracle pinned bit-exact in oracle/make_golden_magvit.py).
+Floating-point tolerance (stated): TF32 products (10-bit mantissa) through ~35 convolutions with GroupNorm in between;
+per-pixel |err| <= 0.08 and mean |err| <= 0.01 on images with std ~0.55, |max| ~3.4 (on average inside one 8-bit pixel
+step after the caller's (x+1)/2 mapping)."""
+import pytest
+import torch
+
+from helpers import load_golden
+from oracle import magvit as OM
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_decode_code_vs_reference_golden(tag):
+    from mmada_parallel_b200.magvit import MAGVITv2
+    g = load_golden("magvit_decode.pt")[tag]
+    cfg = OM.decoder_config(**g["cfg"])
+    w = OM.make_weights(cfg, g["weight_seed"])
+    idx = g["idx"]
+    hw = int(idx.shape[1] ** 0.5)
+    m = MAGVITv2(max_batch=idx.shape[0], ch=cfg.ch, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks, latent_hw=(hw, hw))
+    m.load_state_dict(w)
+    out = m.decode_code(idx)
+    assert tuple(out.shape) == tuple(g["shape"]) and out.dtype == torch.float32
+    s = g["stride"]
+    got = out[:, :, ::s, ::s].cpu()
+    err = (got - g["image"]).abs()
+    print(f"[magvit {tag}] max err {err.max():.4f} mean err {err.mean():.5f} (image std {g['std']:.3f})")
+    assert torch.isfinite(out).all()
+    assert err.max() <= 0.08 and err.mean() <= 0.01
+    assert abs(float(out.mean()) - g["mean"]) < 5e-3 and abs(float(out.std()) - g["std"]) < 5e-3
+    # determinism + batch independence
+    out2 = m.decode_code(idx)
+    assert torch.equal(out, out2)
+    if idx.shape[0] > 1:
+        m1 = MAGVITv2(max_batch=1, ch=cfg.ch, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks, latent_hw=(hw, hw))
+        m1.load_state_dict(w)
+        assert torch.allclose(m1.decode_code(idx[1:2]), out[1:2], atol=1e-5)
+
+
+def test_decode_code_errors():
+    from mmada_parallel_b200 import _lib
+    from mmada_parallel_b200.magvit import MAGVITv2
+    m = MAGVITv2(ch=32, ch_mult=(1, 2), num_res_blocks=(1, 2), latent_hw=(8, 8))
+    with pytest.raises(_lib.MmdpError):  # weights not loaded
+        m.decode_code(torch.zeros(1, 64, dtype=torch.long))
+    with pytest.raises(ValueError):
+        m.decode_code(torch.zeros(1, 60, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        m.get_code(torch.zeros(1, 3, 16, 16))

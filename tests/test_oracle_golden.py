@@ -114,3 +114,15 @@ def test_edge_cases():
     vq[3] = -1
     out = S.image_step("A", cond, None, None, 0.0, 0.0, vq, 126336, 0, 0.0, None, torch.zeros(8, dtype=torch.bfloat16), 8192)
     assert out["mask_len"] == 1 and int(out["masking"].sum()) == 1 and bool(out["masking"][3])
+
+
+def test_magvit_decoder_matches_reference_golden():
+    from oracle import magvit as OM
+    g = load_golden("magvit_decode.pt")["small"]
+    cfg = OM.decoder_config(**g["cfg"])
+    w = OM.make_weights(cfg, g["weight_seed"])
+    out = OM.decode_code(g["idx"], w, cfg)
+    assert tuple(out.shape) == tuple(g["shape"])
+    assert torch.equal(out[:, :, ::g["stride"], ::g["stride"]], g["image"])
+    names = OM.param_shapes(OM.decoder_config())
+    assert sum(torch.Size(s).numel() for s in names.values()) > 39_000_000  # the real decoder (~39.9 M parameters)
