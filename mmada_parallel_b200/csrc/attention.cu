@@ -2,10 +2,12 @@
 // F.scaled_dot_product_attention(q, k, v, attn_mask=None, is_causal=False) at
 // MMaDA-Parallel-A/model/modeling_llada.py:672-679 (M variant :656-663).
 //
-// One CTA = one (batch, head, 128-query tile). Warp roles:
-//   warps 0..3 : softmax / output accumulation (thread t owns query row t == TMEM lane t)
-//   warp 4     : TMA producer (Q once, K and V^T tiles through 2-stage rings) + TMEM allocation
-//   warp 5     : MMA issuer: S = Q·K^T (128x128x128) into a double-buffered TMEM accumulator, PV = P·V into a third
+// One CTA = one (batch, head, 128-query tile). Warp roles (320 threads):
+//   warps 0..7 : softmax / output accumulation. TWO threads per query row: warp w works on TMEM lanes 32*(w%4).. and on
+//                column half w/4 (64 of the 128 S columns of a KV block, 64 of the 128 output columns), so the
+//                exp / FMA instruction stream that bounds this kernel is spread over 8 warps (2 per SM sub-partition).
+//   warp 8     : TMA producer (Q once, K and V^T tiles through 2-stage rings) + TMEM allocation
+//   warp 9     : MMA issuer: S = Q·K^T (128x128x128) into a double-buffered TMEM accumulator, PV = P·V into a third
 // P is written by the softmax threads as bf16 into 128B-swizzled smem (K-major A operand); V is consumed
 // from the transposed layout V^T[b][h][d][token] produced by the QKV GEMM epilogue, so both P·V operands are
 // K-major like every other MMA in this library. O is accumulated in registers (fp32) with the usual
@@ -15,19 +17,22 @@
 
 namespace mmdp {
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 320;
 static constexpr int kHalf = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16 (one swizzle atom wide)
 static constexpr int kTile = 2 * kHalf;     // 32 KB: 128 x 128 bf16
-// smem: Q | K[2] | V[2] | P
-static constexpr int kAttnSmem = kTile * 6 + 1024 + 256;
+// smem: Q | K[2] | V[2] | P | barriers (256 B) | row-exchange scratch (3 KB)
+static constexpr int kAttnSmem = kTile * 6 + 1024 + 256 + 3072;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void softmax_group_sync() {  // the 256 softmax threads only (named barrier 1)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __maxnreg__(200)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
                  float scale_log2) {
@@ -49,13 +54,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint64_t* pv_full = bars + 14;
     uint64_t* pv_empty = bars + 15;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+    float* red_max = reinterpret_cast<float*>(smem + 6 * kTile + 256);  // [2 parity][2 halves][128 rows]
+    float* red_sum = red_max + 2 * 2 * 128;                             // [2 halves][128 rows]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (L + 127) / 128;
 
-    if (warp == 5 && lane == 0) {
+    if (warp == 9 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1);
@@ -63,14 +70,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], 4);
+            mbar_init(&s_empty[s], 8);
         }
-        mbar_init(p_full, 4);
+        mbar_init(p_full, 8);
         mbar_init(pv_full, 1);
-        mbar_init(pv_empty, 4);
+        mbar_init(pv_empty, 8);
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmK);
@@ -85,7 +92,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tS0 = tmem_base, tPV = tmem_base + 256;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             const int qrow0 = b * L + qt * 128;
@@ -107,7 +114,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
@@ -152,37 +159,44 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
     } else {
-        // ===================== softmax + output (warps 0..3) =====================
-        const int r = warp * 32 + lane;  // query row in tile == TMEM lane
-        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-        float o_acc[128];
+        // ===================== softmax + output (warps 0..7) =====================
+        const int lq = warp & 3;   // TMEM lane quarter
+        const int hc = warp >> 2;  // column half owned by this thread (S columns and O columns [64*hc, 64*hc+64))
+        const int r = lq * 32 + lane;  // query row in tile == TMEM lane
+        const uint32_t lane_off = static_cast<uint32_t>(lq * 32) << 16;
+        float o_acc[64];
 #pragma unroll
-        for (int i = 0; i < 128; ++i) o_acc[i] = 0.f;
+        for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
 
         for (int j = 0; j < n_kv; ++j) {
             const int s = j & 1;
             const uint32_t u = (j >> 1) & 1;
-            const int kv0 = j * 128;
-            const int nvalid = L - kv0;  // columns >= nvalid are padding
+            const int nvalid = L - j * 128 - hc * 64;  // valid columns inside this thread's half
             mbar_wait(&s_full[s], u);
             tcgen05_fence_after();
-            const uint32_t tS = tS0 + s * 128 + lane_off;
+            const uint32_t tS = tS0 + s * 128 + hc * 64 + lane_off;
 
-            // pass 1: block row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tS + c * 32, v);
-                tmem_ld_wait();
+            // S row segment (64 fp32) -> registers once; the TMEM buffer is handed back to the MMA warp immediately
+            uint32_t sv[64];
+            tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+            if (nvalid < 64) {  // sequence tail: padding columns become -inf (exp2 -> 0, never the max)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = (c * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
-                    mx = fmaxf(mx, x);
-                }
+                for (int i = 0; i < 64; ++i)
+                    if (i >= nvalid) sv[i] = 0xff800000u;
             }
-            const float m_new = fmaxf(m_run, mx);
+            float mx = __uint_as_float(sv[0]);
+#pragma unroll
+            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            float* rm = red_max + (j & 1) * 256;
+            rm[hc * 128 + r] = mx;
+            softmax_group_sync();
+            const float m_new = fmaxf(m_run, fmaxf(mx, rm[(hc ^ 1) * 128 + r]));
             const float mneg = -m_new * scale_log2;
 
             // consume PV(j-1) (also means the P buffer is free again)
@@ -190,9 +204,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 mbar_wait(pv_full, (j - 1) & 1);
                 tcgen05_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(tPV + lane_off + c * 32, v);
+                    tmem_ld_32x32b_x32(tPV + lane_off + hc * 64 + c * 32, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
@@ -202,52 +216,47 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (lane == 0) mbar_arrive(pv_empty);
             }
 
-            // pass 2: p = exp2((s - m) * scale*log2e) -> bf16 into swizzled smem; row sum
+            // p = exp2((s - m) * scale*log2e) -> bf16 into swizzled smem (half-tile hc); partial row sum
             float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tS + c * 32, v);
-                tmem_ld_wait();
+            uint8_t* prow = sP + hc * kHalf + r * 128;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float p0 = (c * 32 + 2 * i < nvalid) ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, mneg)) : 0.f;
-                    float p1 = (c * 32 + 2 * i + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, mneg)) : 0.f;
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + 2 * i]), scale_log2, mneg));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + 2 * i + 1]), scale_log2, mneg));
                     rs += p0 + p1;
                     pk[i] = pack_bf16x2(p0, p1);
                 }
-                uint8_t* prow = sP + (c >> 1) * kHalf + r * 128;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int lc = (c & 1) * 4 + q;
+                    const int lc = c * 4 + q;
                     *reinterpret_cast<uint4*>(prow + ((lc ^ (r & 7)) << 4)) =
                         make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
-            // S[s] fully read -> MMA may overwrite it with block j+2
-            tcgen05_fence_before();
             fence_proxy_async_smem();  // P stores -> visible to the UMMA (async proxy) read
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&s_empty[s]);
-                mbar_arrive(p_full);
-            }
+            if (lane == 0) mbar_arrive(p_full);
             const float alpha = ex2_approx(fmaf(m_run, scale_log2, mneg));  // exp2((m_old - m_new)*sl2); 0 on the first block
             l_run = fmaf(l_run, alpha, rs);
             m_run = m_new;
             alpha_prev = alpha;
         }
+        // total row sum = the two halves' partial sums (same rescale history)
+        red_sum[hc * 128 + r] = l_run;
+        softmax_group_sync();
+        const float inv_l = 1.0f / (l_run + red_sum[(hc ^ 1) * 128 + r]);
         // last PV
         mbar_wait(pv_full, (n_kv - 1) & 1);
         tcgen05_fence_after();
         const int qrow = qt * 128 + r;
-        const float inv_l = 1.0f / l_run;
-        __nv_bfloat16* orow = out + (size_t)(b * L + (qrow < L ? qrow : 0)) * d_model + h * 128;
+        __nv_bfloat16* orow = out + (size_t)(b * L + (qrow < L ? qrow : 0)) * d_model + h * 128 + hc * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32b_x32(tPV + lane_off + c * 32, v);
+            tmem_ld_32x32b_x32(tPV + lane_off + hc * 64 + c * 32, v);
             tmem_ld_wait();
             if (qrow < L) {
                 uint32_t pk[16];
@@ -266,7 +275,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }

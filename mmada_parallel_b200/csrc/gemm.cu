@@ -16,13 +16,18 @@
 
 namespace mmdp {
 
-static constexpr int BM = 128, BN = 256, BK = 64;
-static constexpr int kStages = 4;
+static constexpr int BM = 128, BK = 64;
 static constexpr int kABytes = BM * BK * 2;  // 16 KB
-static constexpr int kBBytes = BN * BK * 2;  // 32 KB
-static constexpr int kStageBytes = kABytes + kBBytes;
 static constexpr int kGemmThreads = 256;
-static constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// The N tile width is a template parameter: 256 (default; required by the QKV/SwiGLU epilogues) or 192. The K loop and
+// therefore the fp32 accumulation order of every output element is identical for both, so results do not depend on
+// the tile width; the host picks the width that minimises (waves x width) for the problem (wave quantisation on 148 SMs).
+template <int BN> struct GemmCfg {
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : 5;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct GemmParams {
     int M, N, K;
@@ -48,9 +53,12 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
     }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int kStages = GemmCfg<BN>::kStages;
+    constexpr int kStageBytes = GemmCfg<BN>::kStageBytes;
+    static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -287,19 +295,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        MMDP_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        MMDP_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmem));
         attr_set = true;
     }
     const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+    gemm_bf16_kernel<EPI, BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, stream>>>(tmA, tmB, p);
     MMDP_CUDA(cudaGetLastError());
     return 0;
+}
+
+// waves x tile width (plus a small penalty for the narrower tile's lower operand reuse)
+static int pick_tile_n(int M, int N) {
+    const int g = num_sms();
+    const long long m_tiles = (M + BM - 1) / BM;
+    const long long w256 = (m_tiles * ((N + 255) / 256) + g - 1) / g * 256 * 100;
+    const long long w192 = (m_tiles * ((N + 191) / 192) + g - 1) / g * 192 * 104;
+    return w192 < w256 ? 192 : 256;
 }
 
 int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
@@ -312,19 +329,20 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
+    const int bn = (epi == EPI_PLAIN || epi == EPI_RESID) ? pick_tile_n(M, N) : 256;
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;
-    if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN, BK)) return -1;
+    if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn, BK)) return -1;
     switch (epi) {
         case EPI_PLAIN:
             if (!C || (ldc % 8) || (N % 8)) return set_error("gemm: C null or ldc/N not multiple of 8");
-            return launch_gemm<EPI_PLAIN>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_gemm<EPI_PLAIN, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_PLAIN, 256>(tmA, tmB, p, stream);
         case EPI_RESID:
             if (!C || !resid || (ldc % 8) || (ldr % 8) || (N % 8)) return set_error("gemm: bad residual epilogue args");
-            return launch_gemm<EPI_RESID>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_gemm<EPI_RESID, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_RESID, 256>(tmA, tmB, p, stream);
         case EPI_SWIGLU:
             if (!C || (ldc % 8) || (N % 256)) return set_error("gemm: swiglu needs N % 256 == 0 (interleaved gate/up tiles)");
-            return launch_gemm<EPI_SWIGLU>(tmA, tmB, p, stream);
+            return launch_gemm<EPI_SWIGLU, 256>(tmA, tmB, p, stream);
         case EPI_QKVROPE:
             if (!qa) return set_error("gemm: qkv epilogue needs QkvRopeArgs");
             if (qa->d_model % 256 || N != 3 * qa->d_model || qa->d_model != qa->n_heads * 128)
@@ -332,7 +350,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
             if (M % qa->L) return set_error("gemm: qkv epilogue needs M == B*L");
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
-            return launch_gemm<EPI_QKVROPE>(tmA, tmB, p, stream);
+            return launch_gemm<EPI_QKVROPE, 256>(tmA, tmB, p, stream);
         default:
             return set_error("gemm: unknown epilogue");
     }
