@@ -62,6 +62,7 @@ SIGNATURES = {
     "mmdp_prof_enable": (None, [_i]),
     "mmdp_prof_summary": (_i, [_vp, _vp, _vp]),
     "mmdp_launch_count": (C.c_longlong, [_i]),
+    "mmdp_set_gemm_pair": (None, [_i]),
     "mmdp_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "mmdp_qkv_rope": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdp_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

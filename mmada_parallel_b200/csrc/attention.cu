@@ -32,7 +32,7 @@ __device__ __forceinline__ void softmax_group_sync() {  // the 256 softmax threa
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
                  float scale_log2) {

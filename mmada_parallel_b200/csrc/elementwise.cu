@@ -36,15 +36,37 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restri
     uint4* dst = reinterpret_cast<uint4*>(y + (size_t)orow * ldy);
     const int nvec = d / 8;
 
+    // the row stays in registers when it fits (d <= 8192): one HBM/L2 read per element
+    constexpr int kKeep = 4;
+    const bool keep = nvec <= kKeep * 256;
+    uint4 held[kKeep];
     float ss = 0.f;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const uint4 v = src[i];
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
-            ss = fmaf(a, a, ss);
-            ss = fmaf(b, b, ss);
+    for (int t = 0; t < kKeep; ++t) {
+        const int i = threadIdx.x + t * 256;
+        held[t] = (keep && i < nvec) ? src[i] : make_uint4(0, 0, 0, 0);
+    }
+    if (keep) {
+#pragma unroll
+        for (int t = 0; t < kKeep; ++t) {
+            const uint32_t u[4] = {held[t].x, held[t].y, held[t].z, held[t].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+                ss = fmaf(a, a, ss);
+                ss = fmaf(b, b, ss);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const uint4 v = src[i];
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+                ss = fmaf(a, a, ss);
+                ss = fmaf(b, b, ss);
+            }
         }
     }
     __shared__ float red[8];
@@ -57,8 +79,16 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restri
     const float var = tot / (float)d;
     const float rstd = __frcp_rn(__fsqrt_rn(__fadd_rn(var, eps)));  // torch.rsqrt on CPU == 1/sqrt(x)
 
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const uint4 v = src[i];
+    for (int i = threadIdx.x, t = 0; i < nvec; i += blockDim.x, ++t) {
+        uint4 v;
+        if (keep) {
+            v = held[0];
+#pragma unroll
+            for (int q = 1; q < kKeep; ++q)
+                if (t == q) v = held[q];
+        } else {
+            v = src[i];
+        }
         const uint4 wv = w4[i];
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
         const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};

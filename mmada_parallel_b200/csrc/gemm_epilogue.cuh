@@ -1,0 +1,157 @@
+// Fused epilogues of the bf16 GEMM kernels (shared by the 1-CTA kernel in gemm.cu and the CTA-pair kernel in gemm2.cu).
+// One call handles one thread's row of one 128 x BN accumulator tile held in TMEM.
+#pragma once
+#include "mmdp_internal.h"
+#include "ptx.cuh"
+
+namespace mmdp {
+
+struct GemmParams {
+    int M, N, K;
+    __nv_bfloat16* C;
+    int ldc;
+    const __nv_bfloat16* resid;
+    int ldr;
+    // EPI_QKVROPE
+    __nv_bfloat16* q;
+    __nv_bfloat16* k;
+    __nv_bfloat16* vt;
+    const float* cos_tab;  // [L, 64]
+    const float* sin_tab;  // [L, 64]
+    int L, Lpad, d_model, n_heads;
+};
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t (&p)[16], int ncols_valid) {
+    // dst is 16-B aligned when ldc % 8 == 0 and column offsets are multiples of 8
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i * 8 < ncols_valid) d4[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+    }
+}
+
+// tbase: TMEM address of this warp's lane quarter and accumulator stage; row: global output row of this thread;
+// n_blk: N-tile index (tile columns [n_blk*BN, n_blk*BN + BN)).
+template <int EPI, int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t tbase, int row, bool row_ok, int n_blk) {
+            const int n0 = n_blk * BN;
+            if constexpr (EPI == EPI_PLAIN || EPI == EPI_RESID) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tbase + c * 32, v);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * 32;
+                    const int nvalid = p.N - col0;
+                    if (row_ok && nvalid > 0) {
+                        uint32_t pk[16];
+                        if constexpr (EPI == EPI_RESID) {
+                            const uint4* r4 = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col0);
+                            uint32_t rr[16];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 t = (i * 8 < nvalid) ? r4[i] : make_uint4(0, 0, 0, 0);
+                                rr[4 * i] = t.x; rr[4 * i + 1] = t.y; rr[4 * i + 2] = t.z; rr[4 * i + 3] = t.w;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                // nn.Linear output is rounded to bf16 first, then the residual add rounds again
+                                float a0 = bf16_round(__uint_as_float(v[2 * i]));
+                                float a1 = bf16_round(__uint_as_float(v[2 * i + 1]));
+                                pk[i] = pack_bf16x2(__fadd_rn(bf16_lo(rr[i]), a0), __fadd_rn(bf16_hi(rr[i]), a1));
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        }
+                        store_bf16x32(p.C + (size_t)row * p.ldc + col0, pk, nvalid);
+                    }
+                }
+            } else if constexpr (EPI == EPI_SWIGLU) {
+                // tile columns [0,128) = gate rows of W1, [128,256) = up rows of W3 (weights packed interleaved)
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(tbase + c * 32, g);
+                    tmem_ld_32x32b_x32(tbase + 128 + c * 32, u);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * 128 + c * 32;
+                    const int nvalid = p.N / 2 - col0;
+                    if (row_ok && nvalid > 0) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float o[2];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                float gg = bf16_round(__uint_as_float(g[2 * i + h]));
+                                float uu = bf16_round(__uint_as_float(u[2 * i + h]));
+                                float s = bf16_round(__fdiv_rn(gg, __fadd_rn(1.0f, expf(-gg))));  // silu -> bf16
+                                o[h] = __fmul_rn(s, uu);
+                            }
+                            pk[i] = pack_bf16x2(o[0], o[1]);
+                        }
+                        store_bf16x32(p.C + (size_t)row * p.ldc + col0, pk, nvalid);
+                    }
+                }
+            } else if constexpr (EPI == EPI_QKVROPE) {
+                const int region = n0 / p.d_model;  // 0 = Q, 1 = K, 2 = V (d_model % 256 == 0 is checked on the host)
+                const int b = row_ok ? row / p.L : 0;
+                const int pos = row_ok ? row - b * p.L : 0;
+                if (region < 2) {
+                    __nv_bfloat16* dst = (region == 0 ? p.q : p.k) + (size_t)row * p.d_model + (n0 - region * p.d_model);
+#pragma unroll 1
+                    for (int hc = 0; hc < 4; ++hc) {  // (head in tile) x (32-col chunk of the first half)
+                        const int head = hc >> 1, cc = hc & 1;
+                        uint32_t x1[32], x2[32];
+                        tmem_ld_32x32b_x32(tbase + head * 128 + cc * 32, x1);
+                        tmem_ld_32x32b_x32(tbase + head * 128 + 64 + cc * 32, x2);
+                        tmem_ld_wait();
+                        if (row_ok) {
+                            const float4* c4 = reinterpret_cast<const float4*>(p.cos_tab + (size_t)pos * 64 + cc * 32);
+                            const float4* s4 = reinterpret_cast<const float4*>(p.sin_tab + (size_t)pos * 64 + cc * 32);
+                            uint32_t o1[16], o2[16];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 cv = c4[i], sv = s4[i];
+                                const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
+                                const float sn[4] = {sv.x, sv.y, sv.z, sv.w};
+                                float a[4], bb[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float t1 = bf16_round(__uint_as_float(x1[4 * i + j]));
+                                    const float t2 = bf16_round(__uint_as_float(x2[4 * i + j]));
+                                    // (t * cos) + (rotate_half(t) * sin), fp32, no FMA contraction
+                                    a[j] = __fadd_rn(__fmul_rn(t1, cs[j]), __fmul_rn(-t2, sn[j]));
+                                    bb[j] = __fadd_rn(__fmul_rn(t2, cs[j]), __fmul_rn(t1, sn[j]));
+                                }
+                                o1[2 * i] = pack_bf16x2(a[0], a[1]);
+                                o1[2 * i + 1] = pack_bf16x2(a[2], a[3]);
+                                o2[2 * i] = pack_bf16x2(bb[0], bb[1]);
+                                o2[2 * i + 1] = pack_bf16x2(bb[2], bb[3]);
+                            }
+                            store_bf16x32(dst + head * 128 + cc * 32, o1, 32);
+                            store_bf16x32(dst + head * 128 + 64 + cc * 32, o2, 32);
+                        }
+                    }
+                } else {
+                    // V is written transposed: vt[b][head][d][token] so that P·V runs with both operands K-major
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tbase + c * 32, v);
+                        tmem_ld_wait();
+                        if (row_ok) {
+                            const int n = n0 - 2 * p.d_model + c * 32;
+                            const int head = n >> 7, d0 = n & 127;
+                            __nv_bfloat16* dst = p.vt + ((size_t)(b * p.n_heads + head) * 128 + d0) * p.Lpad + pos;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dst[(size_t)i * p.Lpad] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                        }
+                    }
+                }
+            }
+}
+
+}  // namespace mmdp

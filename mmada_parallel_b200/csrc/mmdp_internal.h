@@ -67,6 +67,12 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
               __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa,
               cudaStream_t stream);
 
+// CTA-pair (cta_group::2) kernel, gemm2.cu; selected by MMDP_GEMM_PAIR=1 or mmdp_set_gemm_pair(1)
+int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                   __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa, cudaStream_t stream);
+int gemm_pair_mode();
+void set_gemm_pair_mode(int on);
+
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                   int H, int L, int Lpad, float scale, cudaStream_t stream);
 

@@ -197,7 +197,66 @@ def case_embed_lfq():
     return out
 
 
+def case_pair(M, N, K, epi="plain", timing=True):
+    """CTA-pair (cta_group::2) kernel vs the 1-CTA kernel: same K order -> must be bit-identical."""
+    import torch
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(M + N)
+    dev = "cuda"
+    a = _bf16(torch.randn(M, K, device=dev) * 0.5)
+    w = _bf16(torch.randn(N, K, device=dev) * 0.05)
+    r = _bf16(torch.randn(M, N, device=dev))
+    code = {"plain": _lib.EPI_PLAIN, "resid": _lib.EPI_RESID, "swiglu": _lib.EPI_SWIGLU}[epi]
+    kw = dict(resid=r) if epi == "resid" else {}
+    _lib.lib.mmdp_set_gemm_pair(0)
+    ref = _lib.gemm_bf16(a, w, code, **kw)
+    torch.cuda.synchronize()
+    _lib.lib.mmdp_set_gemm_pair(1)
+    got = _lib.gemm_bf16(a, w, code, **kw)
+    torch.cuda.synchronize()
+    out = stats(f"pair_{epi}_{M}x{N}x{K}", got, ref)
+    out["bit_identical"] = bool(torch.equal(got, ref))
+    out["ok"] = out["bit_identical"]
+    if timing:
+        ms_p = time_it(lambda: _lib.gemm_bf16(a, w, code, out=got, **kw))
+        _lib.lib.mmdp_set_gemm_pair(0)
+        ms_s = time_it(lambda: _lib.gemm_bf16(a, w, code, out=got, **kw))
+        out.update(pair_ms=ms_p, single_ms=ms_s, pair_tflops=2.0 * M * N * K / ms_p / 1e9, single_tflops=2.0 * M * N * K / ms_s / 1e9)
+    return out
+
+
+def case_pair_qkv(B, L, H):
+    import torch
+    from mmada_parallel_b200 import _lib
+    from mmada_parallel_b200.model import rope_tables
+    torch.manual_seed(5)
+    d, M = H * 128, B * L
+    a = _bf16(torch.randn(M, d, device="cuda"))
+    wqkv = _bf16(torch.randn(3 * d, d, device="cuda") / math.sqrt(d))
+    cos, sin = (t.cuda() for t in rope_tables(128, 500000.0, L))
+    _lib.lib.mmdp_set_gemm_pair(0)
+    q0, k0, v0 = _lib.qkv_rope(a, wqkv, H, L, cos, sin)
+    torch.cuda.synchronize()
+    _lib.lib.mmdp_set_gemm_pair(1)
+    q1, k1, v1 = _lib.qkv_rope(a, wqkv, H, L, cos, sin)
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(q0, q1) and torch.equal(k0, k1) and torch.equal(v0, v1))
+    out = {"case": f"pair_qkv_B{B}L{L}H{H}", "bit_identical": ok, "ok": ok}
+    ms_p = time_it(lambda: _lib.qkv_rope(a, wqkv, H, L, cos, sin))
+    _lib.lib.mmdp_set_gemm_pair(0)
+    ms_s = time_it(lambda: _lib.qkv_rope(a, wqkv, H, L, cos, sin))
+    out.update(pair_ms=ms_p, single_ms=ms_s, pair_tflops=2.0 * M * 3 * d * d / ms_p / 1e9, single_tflops=2.0 * M * 3 * d * d / ms_s / 1e9)
+    return out
+
+
 CASES = {
+    "pair_small": lambda: case_pair(512, 512, 256, timing=False),
+    "pair_ragged": lambda: case_pair(777, 1000, 520, timing=False),
+    "pair_resid": lambda: case_pair(2414, 4096, 4096, "resid"),
+    "pair_ffout": lambda: case_pair(2414, 4096, 12288, "resid"),
+    "pair_swiglu": lambda: case_pair(2414, 24576, 4096, "swiglu"),
+    "pair_plain_qkvshape": lambda: case_pair(2414, 12288, 4096),
+    "pair_qkv": lambda: case_pair_qkv(1, 2414, 32),
     "gemm_plain_tile": lambda: case_gemm(128, 256, 64),
     "gemm_plain_k": lambda: case_gemm(128, 256, 512),
     "gemm_plain_multi": lambda: case_gemm(512, 1024, 1024),
