@@ -48,6 +48,7 @@ MMDP_API void mmdp_set_gemm_pair(int on);
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */
 #define MMDP_EPI_PLAIN 0   /* C = bf16(A W^T)                                 nn.Linear, modeling_llada.py:1402      */
 #define MMDP_EPI_RESID 1   /* C = bf16(bf16(A W^T) + R)                       attn_out :744 + :953; ff_out :968+:970  */
+#define MMDP_EPI_F32 4     /* C (float*) = raw fp32 accumulators: tensor-parallel partial sums, all-reduced before rounding      */
 #define MMDP_EPI_SWIGLU 3  /* C = bf16(bf16(silu(bf16 g)) * bf16 u), W rows interleaved 128 gate / 128 up   :962-967 */
 
 /* C[M,N] = A[M,K] * W[N,K]^T, bf16 in, fp32 accumulate (tcgen05/TMEM), fused epilogue.
@@ -62,6 +63,15 @@ MMDP_API int mmdp_gemm_bf16(int epilogue, const uint16_t* A, int lda, const uint
  * cos/sin: fp32 [L, 64] tables (first half of the reference's cat(freqs, freqs) table). head_dim must be 128. */
 MMDP_API int mmdp_qkv_rope(const uint16_t* A, int lda, const uint16_t* Wqkv, int M, int d_model, int n_heads, int L, int Lpad,
                   const float* cos_tab, const float* sin_tab, uint16_t* q, uint16_t* k, uint16_t* vt, void* stream);
+
+/* Tensor-parallel shard of the same projection: Wqkv = [q rows | k rows | v rows] of this rank's n_heads_local heads
+ * ([3*128*n_heads_local, d_model]); q,k: [B*L, 128*n_heads_local]; vt: [B, n_heads_local, 128, Lpad]. */
+MMDP_API int mmdp_qkv_rope_tp(const uint16_t* A, int lda, const uint16_t* Wqkv, int M, int d_model, int n_heads_local, int L,
+                      int Lpad, const float* cos_tab, const float* sin_tab, uint16_t* q, uint16_t* k, uint16_t* vt, void* stream);
+
+/* x = bf16(bf16(partial) + x): residual add of an fp32 partial-sum buffer that was all-reduced across tensor-parallel ranks
+ * (keeps the reference's rounding points: nn.Linear output -> bf16, then the residual add -> bf16). */
+MMDP_API int mmdp_resid_add_f32(uint16_t* x, int ldx, const float* partial, int ldp, int M, int d, void* stream);
 
 /* softmax(q k^T * scale) v, no mask, non-causal (F.scaled_dot_product_attention call at modeling_llada.py:672-679).
  * q,k: [B*L, n_heads*128]; vt: [B, n_heads, 128, Lpad]; out: [B*L, n_heads*128]. */

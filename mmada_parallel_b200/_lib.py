@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmdp.so")
 
-EPI_PLAIN, EPI_RESID, EPI_SWIGLU = 0, 1, 3
+EPI_PLAIN, EPI_RESID, EPI_SWIGLU, EPI_F32 = 0, 1, 3, 4
 
 
 class MmdpError(RuntimeError):
@@ -65,6 +65,8 @@ SIGNATURES = {
     "mmdp_set_gemm_pair": (None, [_i]),
     "mmdp_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "mmdp_qkv_rope": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmdp_qkv_rope_tp": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmdp_resid_add_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "mmdp_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "mmdp_rmsnorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mmdp_embed": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),

@@ -75,7 +75,7 @@ MMDP_API const char* mmdp_last_error(void) { return last_error(); }
 
 MMDP_API int mmdp_gemm_bf16(int epilogue, const uint16_t* A, int lda, const uint16_t* W, int ldw, int M, int N, int K,
                    uint16_t* C, int ldc, const uint16_t* R, int ldr, void* stream) {
-    if (epilogue != MMDP_EPI_PLAIN && epilogue != MMDP_EPI_RESID && epilogue != MMDP_EPI_SWIGLU)
+    if (epilogue != MMDP_EPI_PLAIN && epilogue != MMDP_EPI_RESID && epilogue != MMDP_EPI_SWIGLU && epilogue != MMDP_EPI_F32)
         return set_error("mmdp_gemm_bf16: unknown epilogue %d", epilogue);
     return gemm_bf16(epilogue, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, (bf16*)C, ldc, (const bf16*)R, ldr,
                      nullptr, (cudaStream_t)stream);
@@ -86,6 +86,18 @@ MMDP_API int mmdp_qkv_rope(const uint16_t* A, int lda, const uint16_t* Wqkv, int
     QkvRopeArgs qa{(bf16*)q, (bf16*)k, (bf16*)vt, cos_tab, sin_tab, L, Lpad, d_model, n_heads};
     return gemm_bf16(EPI_QKVROPE, (const bf16*)A, lda, (const bf16*)Wqkv, d_model, M, 3 * d_model, d_model, nullptr, 0,
                      nullptr, 0, &qa, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_qkv_rope_tp(const uint16_t* A, int lda, const uint16_t* Wqkv, int M, int d_model, int n_heads_local, int L,
+                      int Lpad, const float* cos_tab, const float* sin_tab, uint16_t* q, uint16_t* k, uint16_t* vt, void* stream) {
+    const int d_attn = n_heads_local * 128;
+    QkvRopeArgs qa{(bf16*)q, (bf16*)k, (bf16*)vt, cos_tab, sin_tab, L, Lpad, d_attn, n_heads_local};
+    return gemm_bf16(EPI_QKVROPE, (const bf16*)A, lda, (const bf16*)Wqkv, d_model, M, 3 * d_attn, d_model, nullptr, 0, nullptr, 0,
+                     &qa, (cudaStream_t)stream);
+}
+
+MMDP_API int mmdp_resid_add_f32(uint16_t* x, int ldx, const float* partial, int ldp, int M, int d, void* stream) {
+    return resid_add_f32((bf16*)x, ldx, partial, ldp, M, d, (cudaStream_t)stream);
 }
 
 MMDP_API int mmdp_attention(const uint16_t* q, const uint16_t* k, const uint16_t* vt, uint16_t* out, int B, int n_heads, int L,

@@ -32,7 +32,7 @@ __device__ __forceinline__ void softmax_group_sync() {  // the 256 softmax threa
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
                  float scale_log2) {
@@ -177,22 +177,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tcgen05_fence_after();
             const uint32_t tS = tS0 + s * 128 + hc * 64 + lane_off;
 
-            // S row segment (64 fp32) -> registers once; the TMEM buffer is handed back to the MMA warp immediately
-            uint32_t sv[64];
-            tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-            tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[s]);
-            if (nvalid < 64) {  // sequence tail: padding columns become -inf (exp2 -> 0, never the max)
+            // pass 1: row max over this thread's 64 columns (both TMEM loads in flight, one wait)
+            float mx;
+            {
+                uint32_t sv[64];
+                tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+                tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+                tmem_ld_wait();
+                if (nvalid < 64) {  // sequence tail: padding columns never win the max
 #pragma unroll
-                for (int i = 0; i < 64; ++i)
-                    if (i >= nvalid) sv[i] = 0xff800000u;
+                    for (int i = 0; i < 64; ++i)
+                        if (i >= nvalid) sv[i] = 0xff800000u;
+                }
+                mx = __uint_as_float(sv[0]);
+#pragma unroll
+                for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
             }
-            float mx = __uint_as_float(sv[0]);
-#pragma unroll
-            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
             float* rm = red_max + (j & 1) * 256;
             rm[hc * 128 + r] = mx;
             softmax_group_sync();
@@ -217,6 +217,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
 
             // p = exp2((s - m) * scale*log2e) -> bf16 into swizzled smem (half-tile hc); partial row sum
+            // (S is re-read from TMEM instead of being held across the PV update: the register file is allocated per
+            //  4-warp group, which caps this 10-warp CTA at 168 registers per thread)
+            uint32_t sv[64];
+            tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_wait();
+            tcgen05_fence_before();  // S[s] fully read -> the MMA warp may overwrite it with block j+2
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+            if (nvalid < 64) {  // padding columns: exp2(-inf) = 0
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i >= nvalid) sv[i] = 0xff800000u;
+            }
             float rs = 0.f;
             uint8_t* prow = sP + hc * kHalf + r * 128;
 #pragma unroll

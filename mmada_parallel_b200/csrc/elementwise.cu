@@ -113,6 +113,34 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
     return 0;
 }
 
+// x = bf16( bf16(partial_sum) + x ): the rounding points of `x + attn_out(att)` (modeling_llada.py:744,:953) applied to a
+// tensor-parallel partial-sum buffer that has already been all-reduced in fp32.
+__global__ void __launch_bounds__(256) resid_add_f32_kernel(__nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ part,
+                                                             int ldp, int d) {
+    const int row = blockIdx.x;
+    uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
+    const float4* pr = reinterpret_cast<const float4*>(part + (size_t)row * ldp);
+    for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+        uint4 xv = xr[i];
+        const float4 a = pr[2 * i], b = pr[2 * i + 1];
+        const float pf[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t u[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            u[j] = pack_bf16x2(__fadd_rn(bf16_lo(u[j]), bf16_round(pf[2 * j])), __fadd_rn(bf16_hi(u[j]), bf16_round(pf[2 * j + 1])));
+        xr[i] = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+}
+
+int resid_add_f32(__nv_bfloat16* x, int ldx, const float* partial, int ldp, int M, int d, cudaStream_t stream) {
+    if (M <= 0) return 0;
+    if ((d % 8) || (ldx % 8) || (ldp % 4)) return set_error("resid_add_f32: d/ldx must be multiples of 8, ldp of 4");
+    LaunchScope ls(LK_ROW, (double)M * d * 8, stream);
+    resid_add_f32_kernel<<<M, 256, 0, stream>>>(x, ldx, partial, ldp, d);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy, int M, int d, float eps,
             cudaStream_t stream) {
     return rmsnorm_rows(x, ldx, nullptr, w, y, ldy, M, d, eps, stream);

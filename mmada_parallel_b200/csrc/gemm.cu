@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int kStages = GemmCfg<BN>::kStages;
     constexpr int kStageBytes = GemmCfg<BN>::kStageBytes;
-    static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
+    static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || EPI == EPI_F32 || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -203,6 +203,9 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
         case EPI_RESID:
             if (!C || !resid || (ldc % 8) || (ldr % 8) || (N % 8)) return set_error("gemm: bad residual epilogue args");
             break;
+        case EPI_F32:
+            if (!C || (ldc % 4) || (N % 4)) return set_error("gemm: fp32 output needs ldc/N multiples of 4");
+            break;
         case EPI_SWIGLU:
             if (!C || (ldc % 8) || (N % 256)) return set_error("gemm: swiglu needs N % 256 == 0 (interleaved gate/up tiles)");
             break;
@@ -220,7 +223,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
-    const int bn = (epi == EPI_PLAIN || epi == EPI_RESID) ? pick_tile_n(M, N) : 256;
+    const int bn = (epi == EPI_PLAIN || epi == EPI_RESID || epi == EPI_F32) ? pick_tile_n(M, N) : 256;
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;
     if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn, BK)) return -1;
@@ -229,6 +232,8 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
             return bn == 192 ? launch_gemm<EPI_PLAIN, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_PLAIN, 256>(tmA, tmB, p, stream);
         case EPI_RESID:
             return bn == 192 ? launch_gemm<EPI_RESID, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_RESID, 256>(tmA, tmB, p, stream);
+        case EPI_F32:
+            return bn == 192 ? launch_gemm<EPI_F32, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_F32, 256>(tmA, tmB, p, stream);
         case EPI_SWIGLU:
             return launch_gemm<EPI_SWIGLU, 256>(tmA, tmB, p, stream);
         case EPI_QKVROPE:

@@ -79,7 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int kStages = PairCfg<BN>::kStages;
     constexpr int kStageBytes = PairCfg<BN>::kStageBytes;
-    static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
+    static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || EPI == EPI_F32 || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -233,7 +233,7 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
-    const int bn = (epi == EPI_PLAIN || epi == EPI_RESID) ? pick_pair_tile_n(M, N) : 256;
+    const int bn = (epi == EPI_PLAIN || epi == EPI_RESID || epi == EPI_F32) ? pick_pair_tile_n(M, N) : 256;
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, P_BM, P_BK)) return -1;
     if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn / 2, P_BK)) return -1;
@@ -242,6 +242,8 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
             return bn == 192 ? launch_pair<EPI_PLAIN, 192>(tmA, tmB, p, stream) : launch_pair<EPI_PLAIN, 256>(tmA, tmB, p, stream);
         case EPI_RESID:
             return bn == 192 ? launch_pair<EPI_RESID, 192>(tmA, tmB, p, stream) : launch_pair<EPI_RESID, 256>(tmA, tmB, p, stream);
+        case EPI_F32:
+            return bn == 192 ? launch_pair<EPI_F32, 192>(tmA, tmB, p, stream) : launch_pair<EPI_F32, 256>(tmA, tmB, p, stream);
         case EPI_SWIGLU:
             return launch_pair<EPI_SWIGLU, 256>(tmA, tmB, p, stream);
         case EPI_QKVROPE:

@@ -35,7 +35,24 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
 template <int EPI, int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t tbase, int row, bool row_ok, int n_blk) {
             const int n0 = n_blk * BN;
-            if constexpr (EPI == EPI_PLAIN || EPI == EPI_RESID) {
+            if constexpr (EPI == EPI_F32) {
+                // raw fp32 accumulators (tensor-parallel partial sums: reduced across ranks in fp32, rounded once afterwards)
+                float* Cf = reinterpret_cast<float*>(p.C);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tbase + c * 32, v);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * 32;
+                    const int nvalid = p.N - col0;
+                    if (row_ok && nvalid > 0) {
+                        uint4* d4 = reinterpret_cast<uint4*>(Cf + (size_t)row * p.ldc + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i * 4 < nvalid) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+            } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RESID) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t v[32];

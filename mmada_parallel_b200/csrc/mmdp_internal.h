@@ -8,7 +8,7 @@
 
 namespace mmdp {
 
-enum Epilogue { EPI_PLAIN = 0, EPI_RESID = 1, EPI_QKVROPE = 2, EPI_SWIGLU = 3 };
+enum Epilogue { EPI_PLAIN = 0, EPI_RESID = 1, EPI_QKVROPE = 2, EPI_SWIGLU = 3, EPI_F32 = 4 };
 
 int set_error(const char* fmt, ...);  // records the message for mmdp_last_error(), returns -1
 const char* last_error();
@@ -80,6 +80,7 @@ int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, i
                cudaStream_t stream);
 int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy, int M, int d, float eps,
             cudaStream_t stream);
+int resid_add_f32(__nv_bfloat16* x, int ldx, const float* partial, int ldp, int M, int d, cudaStream_t stream);
 int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
                  int M, int d, float eps, cudaStream_t stream);
 
