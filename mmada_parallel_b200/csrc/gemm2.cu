@@ -40,7 +40,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // plain form (as CUTLASS' ClusterBarrier::arrive): an explicit .release.cluster here compiles to MEMBAR.ALL.GPU per
+    // arrival, which throttled the peer's TMA producer to half speed (profiles/r01/README.md, pair-kernel note)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst) {

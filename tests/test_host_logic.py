@@ -71,3 +71,34 @@ def test_replica_sharding_gloo_world2():
         assert p.returncode == 0, e[-2000:]
     assert "OK rank0 shard=[0, 2, 4] max_ms=20.0 total=5" in outs[0][0]
     assert "OK rank1 shard=[1, 3] max_ms=20.0 total=5" in outs[1][0]
+
+
+def test_tensor_parallel_sharding_math():
+    """shard_state_dict: per-rank shards reproduce the full projections (column-parallel outputs concatenate,
+    row-parallel partial products sum) - checked in fp64 on the CPU."""
+    from mmada_parallel_b200.tensor_parallel import shard_state_dict
+    from oracle.llada import make_config, make_weights
+    cfg = make_config(d_model=512, n_heads=4, n_layers=1, mlp_hidden_size=1024, vocab_size=1024)
+    sd = {k: v.double() for k, v in make_weights(cfg, 3).items()}
+    tp, d = 2, cfg.d_model
+    shards = [shard_state_dict(sd, 1, cfg.n_heads, r, tp, vq_col0=512, vq_cols=256) for r in range(tp)]
+    x = torch.randn(7, d, dtype=torch.float64)
+    p = "model.transformer.blocks.0."
+    q_full = x @ sd[p + "q_proj.weight"].t()
+    da = d // tp
+    q_cat = torch.cat([x @ sh["blocks.0.wqkv"][:da].t() for sh in shards], dim=1)
+    v_cat = torch.cat([x @ sh["blocks.0.wqkv"][2 * da:].t() for sh in shards], dim=1)
+    assert torch.allclose(q_cat, q_full) and torch.allclose(v_cat, x @ sd[p + "v_proj.weight"].t())
+    att = torch.randn(7, d, dtype=torch.float64)
+    part = sum(att[:, r * da:(r + 1) * da] @ shards[r]["blocks.0.wo"].t() for r in range(tp))
+    assert torch.allclose(part, att @ sd[p + "attn_out.weight"].t())
+    # SwiGLU shard: interleaved 128-row gate/up blocks, then the row-parallel ff_out partials sum to the full MLP
+    def mlp_local(sh):
+        w13 = sh["blocks.0.w13"].reshape(-1, 2, 128, d)
+        g, u = x @ w13[:, 0].reshape(-1, d).t(), x @ w13[:, 1].reshape(-1, d).t()
+        return (torch.nn.functional.silu(g) * u) @ sh["blocks.0.w2"].t()
+    full = (torch.nn.functional.silu(x @ sd[p + "ff_proj.weight"].t()) * (x @ sd[p + "up_proj.weight"].t())) @ sd[p + "ff_out.weight"].t()
+    assert torch.allclose(sum(mlp_local(sh) for sh in shards), full)
+    head = sd["model.transformer.ff_out.weight"]
+    assert torch.equal(torch.cat([sh["head"] for sh in shards]), head)
+    assert torch.equal(torch.cat([sh["head_vq"] for sh in shards]), head[512:768])
