@@ -28,6 +28,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA/ALU pipes (x <= 0): the SFU executes only 16 ex2 per clock per SM, which bounds a 128x128 score
+// block at 1024 cycles - the same as its two MMAs. Routing every 4th element through this polynomial keeps both pipes
+// busy. Round-to-nearest split x = n + f (|f| <= 0.5), degree-3 minimax for 2^f (max rel. error 7.5e-5, far below the
+// bf16 rounding of P), exponent inserted with integer adds.
+__device__ __forceinline__ float ex2_fma(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;                    // 1.5 * 2^23: integer part of x lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(0.0551716573536396f, f, 0.2426111251115799f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));  // (t bits - magic) << 23 == n << 23 (mod 2^32)
+}
 __device__ __forceinline__ void softmax_group_sync() {  // the 256 softmax threads only (named barrier 1)
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
@@ -189,9 +202,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     for (int i = 0; i < 64; ++i)
                         if (i >= nvalid) sv[i] = 0xff800000u;
                 }
-                mx = __uint_as_float(sv[0]);
+                // 8 independent max chains (a single chain of 64 dependent FMNMX costs ~250 cycles of latency)
+                float m8[8];
 #pragma unroll
-                for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                for (int i = 0; i < 8; ++i) m8[i] = __uint_as_float(sv[i]);
+#pragma unroll
+                for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(sv[i]));
+                mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
             }
             float* rm = red_max + (j & 1) * 256;
             rm[hc * 128 + r] = mx;
@@ -203,17 +220,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (j >= 1) {
                 mbar_wait(pv_full, (j - 1) & 1);
                 tcgen05_fence_after();
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tPV + lane_off + hc * 64 + c * 32, v);
+                {
+                    uint32_t v[64];
+                    tmem_ld_32x32b_x32(tPV + lane_off + hc * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                    tmem_ld_32x32b_x32(tPV + lane_off + hc * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                     tmem_ld_wait();
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pv_empty);  // PV accumulator is in registers: the MMA warp may reuse it
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+                    for (int i = 0; i < 64; ++i) o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(v[i]));
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pv_empty);
             }
 
             // p = exp2((s - m) * scale*log2e) -> bf16 into swizzled smem (half-tile hc); partial row sum
@@ -231,7 +248,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 for (int i = 0; i < 64; ++i)
                     if (i >= nvalid) sv[i] = 0xff800000u;
             }
-            float rs = 0.f;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
             uint8_t* prow = sP + hc * kHalf + r * 128;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -239,8 +256,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + 2 * i]), scale_log2, mneg));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + 2 * i + 1]), scale_log2, mneg));
-                    rs += p0 + p1;
+                    const float a1 = fmaf(__uint_as_float(sv[c * 32 + 2 * i + 1]), scale_log2, mneg);
+                    const float p1 = (i & 1) ? ex2_fma(a1) : ex2_approx(a1);  // every 4th element on the FMA pipe
+                    rs4[i & 3] += p0 + p1;
                     pk[i] = pack_bf16x2(p0, p1);
                 }
 #pragma unroll
@@ -250,6 +268,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
+            const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
             fence_proxy_async_smem();  // P stores -> visible to the UMMA (async proxy) read
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
