@@ -193,40 +193,63 @@ def workload_config(args, n_gpus):
     return {"workload": "MMaDA-Parallel-A 8B, 1 prompt per GPU, 512x512 (1024 VQ tokens) + 256 text tokens, timesteps=64, "
                         "text_steps=128, cfg_img=4.0, cfg_scale=0, temperature=1.0, text_temperature=0 (BASELINE configs[1]"
                         + ("; TINY MODEL - plumbing check only, not a valid number" if args.tiny else "") + ")",
-            "seq_len": 2414, "forwards_per_sample": 192, "parallelism": f"replicas x{n_gpus} (independent prompts, no collective)",
+            "seq_len": 2414, "forwards_per_sample": 192,
+            "parallelism": (f"tensor-parallel x{n_gpus} (one prompt; heads/ff/vocab split, fp32 all-reduce over NCCL)" if getattr(args, "tp", False) and n_gpus > 1
+                            else f"replicas x{n_gpus} (independent prompts, no collective)"),
             "weights": "synthetic normal(0, 0.02) bf16, seeded", "l2": "16.2 GB of weights streamed per forward >> 126 MB L2 (no flush needed)"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
-def build_model(model_cfg: dict, device: str, seed: int):
+def model_namespace(model_cfg: dict):
     from types import SimpleNamespace
-    from mmada_parallel_b200.model import LLaDAForMultiModalGeneration
-    cfg = SimpleNamespace(**model_cfg, n_kv_heads=None, embedding_size=model_cfg["vocab_size"], rope_theta=500000.0,
-                          rms_norm_eps=1e-5, rope=True, rope_full_precision=True, include_bias=False, weight_tying=False)
-    m = LLaDAForMultiModalGeneration(cfg, max_seq_len=model_cfg["max_sequence_length"], max_batch=1, device=device)
+    return SimpleNamespace(**model_cfg, n_kv_heads=None, embedding_size=model_cfg["vocab_size"], rope_theta=500000.0,
+                           rms_norm_eps=1e-5, rope=True, rope_full_precision=True, include_bias=False, weight_tying=False)
+
+
+def synthetic_tensors(model_cfg: dict, device: str, seed: int):
+    """Yields (HF name, bf16 tensor on `device`) of a seeded random-init model: normal(0, 0.02) matrices, unit norms."""
     g = torch.Generator(device=device).manual_seed(seed)
-    d, ff, V = cfg.d_model, cfg.mlp_hidden_size, cfg.vocab_size
+    d, ff, V = model_cfg["d_model"], model_cfg["mlp_hidden_size"], model_cfg["vocab_size"]
 
-    def put(name, *shape, ones=False):
-        t = torch.ones(shape, dtype=torch.bfloat16, device=device) if ones else \
-            torch.empty(shape, dtype=torch.bfloat16, device=device).normal_(0.0, 0.02, generator=g)
-        assert m.set_weight(name, t)
+    def mk(*shape, ones=False):
+        if ones:
+            return torch.ones(shape, dtype=torch.bfloat16, device=device)
+        return torch.empty(shape, dtype=torch.bfloat16, device=device).normal_(0.0, 0.02, generator=g)
 
-    put("model.transformer.wte.weight", V, d)
-    put("model.transformer.ff_out.weight", V, d)
-    put("model.transformer.ln_f.weight", d, ones=True)
-    for i in range(cfg.n_layers):
+    yield "model.transformer.wte.weight", mk(V, d)
+    yield "model.transformer.ff_out.weight", mk(V, d)
+    yield "model.transformer.ln_f.weight", mk(d, ones=True)
+    for i in range(model_cfg["n_layers"]):
         p = f"model.transformer.blocks.{i}."
         for n in ("q_proj", "k_proj", "v_proj", "attn_out"):
-            put(p + n + ".weight", d, d)
-        put(p + "ff_proj.weight", ff, d)
-        put(p + "up_proj.weight", ff, d)
-        put(p + "ff_out.weight", d, ff)
-        put(p + "attn_norm.weight", d, ones=True)
-        put(p + "ff_norm.weight", d, ones=True)
+            yield p + n + ".weight", mk(d, d)
+        yield p + "ff_proj.weight", mk(ff, d)
+        yield p + "up_proj.weight", mk(ff, d)
+        yield p + "ff_out.weight", mk(d, ff)
+        yield p + "attn_norm.weight", mk(d, ones=True)
+        yield p + "ff_norm.weight", mk(d, ones=True)
+
+
+def build_model(model_cfg: dict, device: str, seed: int):
+    from mmada_parallel_b200.model import LLaDAForMultiModalGeneration
+    m = LLaDAForMultiModalGeneration(model_namespace(model_cfg), max_seq_len=model_cfg["max_sequence_length"], max_batch=1, device=device)
+    for name, t in synthetic_tensors(model_cfg, device, seed):
+        assert m.set_weight(name, t)
     m.load_state_dict({}, strict=True)
+    torch.cuda.synchronize()
+    return m
+
+
+def build_tp_model(model_cfg: dict, device: str, seed: int, rank: int, world: int):
+    """Tensor-parallel model (BASELINE config 4): every rank materialises the same seeded tensors and keeps its shard."""
+    from mmada_parallel_b200.tensor_parallel import TensorParallelLLaDA
+    sd = dict(synthetic_tensors(model_cfg, device, seed))
+    m = TensorParallelLLaDA(model_namespace(model_cfg), sd, rank, world, max_seq_len=model_cfg["max_sequence_length"], device=device,
+                            text_vocab_size=TEXT_VOCAB, codebook_size=CODEBOOK)
+    del sd
+    torch.cuda.empty_cache()
     torch.cuda.synchronize()
     return m
 
@@ -246,6 +269,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiny", action="store_true", help="2-layer d=256 model: plumbing check only (INVALID as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp", action="store_true", help="N > 1: ONE sample tensor-parallel over the N GPUs (strong scaling, NCCL "
+                    "all-reduce) instead of N independent replicas")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,8 +291,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(device))
     model_cfg = MODEL_TINY if args.tiny else MODEL_8B
-    model = build_model(model_cfg, device, seed=1000)
-    lay = synthetic_layout(seed=rank)  # every rank denoises its own prompt
+    tp_mode = args.tp and world > 1
+    if tp_mode:
+        model = build_tp_model(model_cfg, device, 1000, rank, world)
+        lay = synthetic_layout(seed=0)  # ONE prompt, all ranks work on it
+    else:
+        model = build_model(model_cfg, device, seed=1000)
+        lay = synthetic_layout(seed=rank)  # every rank denoises its own prompt
     host_ids = lay["input_ids"].pin_memory()
     pos_args = {k: lay[k] for k in ("text_start", "text_end", "image_start", "seq_len", "newline_every")}
     gen = GEN
@@ -284,7 +314,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rng = torch.Generator(device=device).manual_seed(42 + rank)
+    rng = torch.Generator(device=device).manual_seed(42 if tp_mode else 42 + rank)  # TP ranks must draw identical noise
     with torch.no_grad():
         for _ in range(args.warmup):
             denoise_loop(new_state(), generator=rng, **loop_kw)
@@ -333,7 +363,8 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    total_tokens = world * args.steps * TOKENS_PER_SAMPLE
+    n_samples = args.steps if tp_mode else world * args.steps
+    total_tokens = n_samples * TOKENS_PER_SAMPLE
     value = total_tokens / (ms_value / 1e3)
     e2e_value = total_tokens / (ms_e2e / 1e3)
     peaks = {}
@@ -356,8 +387,9 @@ def main():
     flops_sample = algorithmic_flops_per_sample(model_cfg)
     out = {
         "metric": "denoised_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+        "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+        "scaling": "strong" if tp_mode else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
@@ -370,8 +402,8 @@ def main():
                                            "attention_tflops": att_flops / (att_ms / 1e3) / 1e12 if att_ms else None,
                                            "row_GBps": row_bytes / (row_ms / 1e3) / 1e9 if row_ms else None,
                                            "sampling_GBps": smp_bytes / (smp_ms / 1e3) / 1e9 if smp_ms else None},
-        "whole_step_tflops_minimal_work": flops_sample * world * args.steps / (ms_value / 1e3) / 1e12,
-        "whole_step_frac_of_peak": flops_sample * world * args.steps / (ms_value / 1e3) / 1e12 / peak_tf,
+        "whole_step_tflops_minimal_work": flops_sample * n_samples / (ms_value / 1e3) / 1e12,
+        "whole_step_frac_of_peak": flops_sample * n_samples / (ms_value / 1e3) / 1e12 / (peak_tf * world),  # per-GPU fraction
     }
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_sample(model_cfg)
