@@ -43,6 +43,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    volatile int* sk_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -72,15 +73,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_n = (p.N + BN - 1) / BN;
     const int num_k = (p.K + BK - 1) / BK;
     const int num_tiles = num_m * num_n;
+    // tiles [0, full_tiles) are computed whole (persistent loop); the remaining p.sk_tail tiles - a partial last wave -
+    // are split along K: unit u = blockIdx.x handles tile full_tiles + u / splits, k-blocks [kb0, kb1)
+    const int full_tiles = num_tiles - p.sk_tail;
+    const bool has_unit = p.sk_tail > 0 && (int)blockIdx.x < p.sk_tail * p.sk_splits;
+    const int unit_t = has_unit ? (int)blockIdx.x / p.sk_splits : 0;
+    const int unit_s = has_unit ? (int)blockIdx.x - unit_t * p.sk_splits : 0;
+    const int unit_tile = full_tiles + unit_t;
+    const int unit_kb0 = unit_s * p.sk_kb_per;
+    const int unit_kb1 = (unit_kb0 + p.sk_kb_per < num_k) ? unit_kb0 + p.sk_kb_per : num_k;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % num_m, n_blk = tile / num_m;
-                for (int kb = 0; kb < num_k; ++kb) {
+            for (int tile = blockIdx.x; tile < full_tiles + (has_unit ? 1 : 0) * gridDim.x; tile += gridDim.x) {
+                const bool is_unit = tile >= full_tiles;
+                const int tl = is_unit ? unit_tile : tile;
+                const int m_blk = tl % num_m, n_blk = tl / num_m;
+                const int kb_beg = is_unit ? unit_kb0 : 0, kb_end = is_unit ? unit_kb1 : num_k;
+                for (int kb = kb_beg; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], kStageBytes);
                     uint8_t* sa = smem + s * kStageBytes;
@@ -88,6 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kb * BK, n_blk * BN);
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
+                if (is_unit) break;
             }
         }
         __syncwarp();
@@ -99,11 +113,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < full_tiles + (has_unit ? 1 : 0) * gridDim.x; tile += gridDim.x) {
+                const bool is_unit = tile >= full_tiles;
+                const int kb_beg = is_unit ? unit_kb0 : 0, kb_end = is_unit ? unit_kb1 : num_k;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                for (int kb = kb_beg; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + s * kStageBytes);
@@ -112,13 +128,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 bytes per 16 bf16 of K inside the 128-B swizzle atom
-                        umma_bf16_ss(d_tmem, adesc + (k * 2), bdesc + (k * 2), idesc, (kb | k) != 0);
+                        umma_bf16_ss(d_tmem, adesc + (k * 2), bdesc + (k * 2), idesc, ((kb - kb_beg) | k) != 0);
                     }
                     umma_commit(&empty_bar[s]);
-                    if (kb == num_k - 1) umma_commit(&tmem_full[as]);
+                    if (kb == kb_end - 1) umma_commit(&tmem_full[as]);
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
                 if (++as == 2) { as = 0; aph ^= 1; }
+                if (is_unit) break;
             }
         }
         __syncwarp();
@@ -127,19 +144,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
         int as = 0;
         uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int tile = blockIdx.x; tile < full_tiles + (has_unit ? 1 : 0) * gridDim.x; tile += gridDim.x) {
+            const bool is_unit = tile >= full_tiles;
+            const int tl = is_unit ? unit_tile : tile;
+            const int m_blk = tl % num_m, n_blk = tl / num_m;
             mbar_wait(&tmem_full[as], aph);
             tcgen05_fence_after();
             const int row = m_blk * BM + ew * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-            gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk);
+            bool run_epilogue = true;
+            if (is_unit) {
+                // (1) publish this unit's partial accumulator
+                const int rit = ew * 32 + lane;  // row in tile
+                float* my = p.sk_ws + ((size_t)(unit_t * p.sk_splits + unit_s) * BM + rit) * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tbase + c * 32, v);
+                    tmem_ld_wait();
+                    uint4* d4 = reinterpret_cast<uint4*>(my + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                __threadfence();
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps
+                if (ew == 0 && lane == 0) {
+                    const int old = atomicAdd(p.sk_cnt + unit_t, 1);
+                    const int last = old == p.sk_splits - 1;
+                    if (last) p.sk_cnt[unit_t] = 0;  // ready for the next launch
+                    *sk_flag = last;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                run_epilogue = *sk_flag != 0;
+                if (run_epilogue) {
+                    // (2) last arriver: reduce all partials in fixed split order (deterministic), put the sum back into TMEM
+                    __threadfence();
+                    const float* base = p.sk_ws + ((size_t)unit_t * p.sk_splits * BM + rit) * BN;
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        float acc[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                        for (int sp = 0; sp < p.sk_splits; ++sp) {
+                            const float4* s4 = reinterpret_cast<const float4*>(base + (size_t)sp * BM * BN + c * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 t = __ldcg(s4 + i);
+                                acc[4 * i] += t.x; acc[4 * i + 1] += t.y; acc[4 * i + 2] += t.z; acc[4 * i + 3] += t.w;
+                            }
+                        }
+                        uint32_t v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[i]);
+                        tmem_st_32x32b_x32(tbase + c * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            if (run_epilogue) gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk);
             // all TMEM reads of this accumulator stage are complete (wait::ld above) -> hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
             if (++as == 2) { as = 0; aph ^= 1; }
+            if (is_unit) break;
         }
     }
 
@@ -155,27 +224,69 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         MMDP_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmem));
         attr_set = true;
     }
-    const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
     gemm_bf16_kernel<EPI, BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, stream>>>(tmA, tmB, p);
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }
 
-// waves x tile width (plus a small penalty for the narrower tile's lower operand reuse)
-static int pick_tile_n(int M, int N) {
+// Launch plan: tile width (256 | 192), grid, and the split-K tail. Cost model = tile width x (full waves + tail), where a
+// split tail costs 1/splits of a wave plus the partial-sum exchange. Split-K changes the fp32 summation ORDER of the
+// affected tiles (not the rounding points), so it is enabled only for the residual GEMMs of the transformer body
+// (whose shapes are the same in every forward of a run) and can be disabled with MMDP_GEMM_SPLITK=0.
+struct GemmPlan { int bn, grid, tail, splits, kb_per; };
+static int g_splitk_mode = -1;
+static GemmPlan plan_gemm(int epi, int M, int N, int K) {
+    if (g_splitk_mode < 0) {
+        const char* e = getenv("MMDP_GEMM_SPLITK");
+        g_splitk_mode = (e && e[0] == '0') ? 0 : 1;
+    }
     const int g = num_sms();
-    const long long m_tiles = (M + BM - 1) / BM;
-    const long long w256 = (m_tiles * ((N + 255) / 256) + g - 1) / g * 256 * 100;
-    const long long w192 = (m_tiles * ((N + 191) / 192) + g - 1) / g * 192 * 104;
-    return w192 < w256 ? 192 : 256;
+    const int num_k = (K + BK - 1) / BK;
+    const bool flexible = epi == EPI_PLAIN || epi == EPI_RESID || epi == EPI_F32;
+    const bool may_split = g_splitk_mode && epi == EPI_RESID && num_k >= 4;
+    GemmPlan best{256, 0, 0, 0, 0};
+    double best_cost = 1e30;
+    for (int bn : {256, 192}) {
+        if (bn == 192 && !flexible) continue;
+        const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+        GemmPlan pl{bn, tiles < g ? tiles : g, 0, 0, 0};
+        double waves;
+        const int full = tiles >= g ? (tiles / g) * g : 0;
+        const int tail = tiles - full;
+        waves = (double)((tiles + g - 1) / g);
+        if (may_split && tail > 0 && tail * 2 <= g) {
+            int splits = g / tail;
+            if (splits > num_k / 2) splits = num_k / 2;
+            if (splits >= 2) {
+                const int kb_per = (num_k + splits - 1) / splits;
+                splits = (num_k + kb_per - 1) / kb_per;
+                pl.tail = tail; pl.splits = splits; pl.kb_per = kb_per;
+                pl.grid = full > 0 ? g : tail * splits;
+                waves = (double)(full / g) + (double)kb_per / num_k + 0.06;
+            }
+        }
+        const double cost = waves * bn * (bn == 192 ? 1.04 : 1.0);
+        if (cost < best_cost) { best_cost = cost; best = pl; }
+    }
+    return best;
+}
+
+static float* g_sk_ws = nullptr;
+static int* g_sk_cnt = nullptr;
+static int ensure_splitk_workspace() {
+    if (g_sk_ws) return 0;
+    const size_t units = 256;  // >= number of SMs
+    MMDP_CUDA(cudaMalloc(&g_sk_ws, units * BM * 256 * sizeof(float)));
+    MMDP_CUDA(cudaMalloc(&g_sk_cnt, units * sizeof(int)));
+    MMDP_CUDA(cudaMemset(g_sk_cnt, 0, units * sizeof(int)));
+    return 0;
 }
 
 static int g_pair_mode = -1;
@@ -223,23 +334,28 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
-    const int bn = (epi == EPI_PLAIN || epi == EPI_RESID || epi == EPI_F32) ? pick_tile_n(M, N) : 256;
+    const GemmPlan pl = plan_gemm(epi, M, N, K);
+    const int bn = pl.bn, grid = pl.grid;
+    if (pl.tail > 0) {
+        if (ensure_splitk_workspace()) return -1;
+        p.sk_tail = pl.tail; p.sk_splits = pl.splits; p.sk_kb_per = pl.kb_per; p.sk_ws = g_sk_ws; p.sk_cnt = g_sk_cnt;
+    }
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;
     if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn, BK)) return -1;
     switch (epi) {
         case EPI_PLAIN:
-            return bn == 192 ? launch_gemm<EPI_PLAIN, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_PLAIN, 256>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_gemm<EPI_PLAIN, 192>(tmA, tmB, p, grid, stream) : launch_gemm<EPI_PLAIN, 256>(tmA, tmB, p, grid, stream);
         case EPI_RESID:
-            return bn == 192 ? launch_gemm<EPI_RESID, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_RESID, 256>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_gemm<EPI_RESID, 192>(tmA, tmB, p, grid, stream) : launch_gemm<EPI_RESID, 256>(tmA, tmB, p, grid, stream);
         case EPI_F32:
-            return bn == 192 ? launch_gemm<EPI_F32, 192>(tmA, tmB, p, stream) : launch_gemm<EPI_F32, 256>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_gemm<EPI_F32, 192>(tmA, tmB, p, grid, stream) : launch_gemm<EPI_F32, 256>(tmA, tmB, p, grid, stream);
         case EPI_SWIGLU:
-            return launch_gemm<EPI_SWIGLU, 256>(tmA, tmB, p, stream);
+            return launch_gemm<EPI_SWIGLU, 256>(tmA, tmB, p, grid, stream);
         case EPI_QKVROPE:
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
-            return launch_gemm<EPI_QKVROPE, 256>(tmA, tmB, p, stream);
+            return launch_gemm<EPI_QKVROPE, 256>(tmA, tmB, p, grid, stream);
         default:
             return set_error("gemm: unknown epilogue");
     }

@@ -19,6 +19,11 @@ struct GemmParams {
     const float* cos_tab;  // [L, 64]
     const float* sin_tab;  // [L, 64]
     int L, Lpad, d_model, n_heads;
+    // split-K tail (gemm.cu): the last `sk_tail` tiles (a partial wave) are split along K into `sk_splits` units of
+    // `sk_kb_per` k-blocks; partial accumulators meet in `sk_ws` (fp32 [tail][splits][128][BN]), `sk_cnt[tile]` counts arrivals
+    int sk_tail, sk_splits, sk_kb_per;
+    float* sk_ws;
+    int* sk_cnt;
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t (&p)[16], int ncols_valid) {

@@ -109,6 +109,18 @@ def case_gemm(M, N, K, epi="plain", seed=0, timing=False):
     return out
 
 
+def time_resid(M, N, K):
+    import torch
+    from mmada_parallel_b200 import _lib
+    a = _bf16(torch.randn(M, K, device="cuda") * 0.5)
+    w = _bf16(torch.randn(N, K, device="cuda") * 0.05)
+    r = _bf16(torch.randn(M, N, device="cuda"))
+    out = torch.empty_like(r)
+    ms = time_it(lambda: _lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r, out=out))
+    ms_t = time_it(lambda: torch.addmm(r, a, w.t()))
+    return {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "torch_addmm_ms": ms_t, "torch_tflops": 2.0 * M * N * K / ms_t / 1e9}
+
+
 def ref_rope(t, cos, sin):
     """t: [M, H, 128] bf16; cos/sin [M, 64] fp32 -> reference apply_rotary_pos_emb in fp32."""
     import torch
@@ -250,6 +262,10 @@ def case_pair_qkv(B, L, H):
 
 
 CASES = {
+    "splitk_resid_attnout": lambda: case_gemm(2414, 4096, 4096, "resid", timing=False) | time_resid(2414, 4096, 4096),
+    "splitk_resid_ffout": lambda: case_gemm(2414, 4096, 12288, "resid", timing=False) | time_resid(2414, 4096, 12288),
+    "splitk_resid_small": lambda: case_gemm(300, 512, 768, "resid"),
+    "splitk_resid_b2": lambda: case_gemm(4828, 4096, 4096, "resid"),
     "pair_small": lambda: case_pair(512, 512, 256, timing=False),
     "pair_ragged": lambda: case_pair(777, 1000, 520, timing=False),
     "pair_resid": lambda: case_pair(2414, 4096, 4096, "resid"),
