@@ -352,7 +352,7 @@ def main():
 
         # ---- roofline pass (rank 0): one sample with every launch bracketed by CUDA events
         prof = None
-        if rank == 0:
+        if rank == 0 or tp_mode:  # tensor-parallel: every rank must take part (the forward contains collectives)
             _lib.lib.mmdp_prof_enable(1)
             denoise_loop(new_state(), generator=rng, **loop_kw)
             prof = _lib.prof_summary()
