@@ -261,6 +261,70 @@ def algorithmic_flops_per_sample(c: dict, L: int = 2414):
     return 192 * body + 128 * head_text + 128 * head_img  # minimal-equivalent work
 
 
+def run_variant_m(args, rank, local_rank, world):
+    """Extra measurement (not the contract line): variant M, one prompt per GPU, L = 2341, B = 2 (cond + uncond) on every
+    one of the 128 steps, 64 image steps (SURVEY.md 8d synthetic input M). Public API call with host inputs = e2e."""
+    from types import SimpleNamespace
+    import torch.distributed as dist
+    from mmada_parallel_b200.mmada import MMadaModelLM
+    from mmada_parallel_b200.parallel import max_over_ranks
+    device = f"cuda:{local_rank}"
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(device))
+    model_cfg = MODEL_TINY if args.tiny else MODEL_8B
+    ns = model_namespace(model_cfg)
+    ns.mask_token_id = MASK
+    m = MMadaModelLM(ns, max_seq_len=model_cfg["max_sequence_length"], max_batch=2, device=device)
+    for name, t in synthetic_tensors(model_cfg, device, 1000):
+        assert m.set_weight(name, t)
+    m.load_state_dict({}, strict=True)
+    g = torch.Generator().manual_seed(rank)
+    tvoc, soi, eoi, bos = 126349, 126085, 126086, 126080
+    inp = torch.cat([torch.tensor([126340, soi]), torch.randint(tvoc, tvoc + CODEBOOK, (1024,), generator=g), torch.tensor([eoi]),
+                     torch.randint(0, 126000, (32,), generator=g)])
+    unc = inp.clone()
+    unc[-32:] = torch.randint(0, 126000, (32,), generator=g)
+    conf = SimpleNamespace(model=SimpleNamespace(mmada=SimpleNamespace(num_vq_tokens=1024, codebook_size=CODEBOOK)),
+                           dataset=SimpleNamespace(preprocessing=SimpleNamespace(max_seq_length=256)))
+
+    class Tok:
+        bos_token_id = bos
+
+        def __len__(self):
+            return tvoc
+
+    kw = dict(input_ids=inp, uncond_input_ids=unc, text_cfg=2.5, image_cfg=4.0, text_steps=128, image_steps=64,
+              reserved_token_mapping={"<|soi|>": soi, "<|eoi|>": eoi}, config=conf, uni_prompting=SimpleNamespace(text_tokenizer=Tok()))
+    rng = torch.Generator(device=device).manual_seed(42 + rank)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            m.interleave_generate(generator=rng, **kw)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            img, txt = m.interleave_generate(generator=rng, **kw)
+            txt.cpu()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), device=device)
+    if rank == 0:
+        v = world * args.steps * TOKENS_PER_SAMPLE / (ms / 1e3)
+        print(json.dumps({"metric": "denoised_tokens_per_sec", "value": v, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "MMaDA-Parallel-M 8B (extra line, not the contract metric): 1 prompt per GPU, L=2341, CFG batch 2 on "
+                                                 "each of 128 steps, 64 image steps, text_cfg=2.5, image_cfg=4.0", "parallelism": f"replicas x{world}"},
+                          "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": int(inp.numel() * 16), "d2h_bytes_per_step": 256 * 8}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +333,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiny", action="store_true", help="2-layer d=256 model: plumbing check only (INVALID as a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="a", choices=["a", "m"], help="a = BASELINE configs[1] (the contract metric); m = extra line for "
+                    "variant M (interleave_generate, CFG batch 2 every step, BASELINE configs[4] per GPU)")
     ap.add_argument("--tp", action="store_true", help="N > 1: ONE sample tensor-parallel over the N GPUs (strong scaling, NCCL "
                     "all-reduce) instead of N independent replicas")
     args = ap.parse_args()
@@ -277,6 +343,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.variant == "m":
+        run_variant_m(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist

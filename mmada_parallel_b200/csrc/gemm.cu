@@ -155,51 +155,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
             bool run_epilogue = true;
             if (is_unit) {
-                // (1) publish this unit's partial accumulator
-                const int rit = ew * 32 + lane;  // row in tile
-                float* my = p.sk_ws + ((size_t)(unit_t * p.sk_splits + unit_s) * BM + rit) * BN;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tbase + c * 32, v);
-                    tmem_ld_wait();
-                    uint4* d4 = reinterpret_cast<uint4*>(my + c * 32);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
-                __threadfence();
-                asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps
-                if (ew == 0 && lane == 0) {
-                    const int old = atomicAdd(p.sk_cnt + unit_t, 1);
-                    const int last = old == p.sk_splits - 1;
-                    if (last) p.sk_cnt[unit_t] = 0;  // ready for the next launch
-                    *sk_flag = last;
-                }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                run_epilogue = *sk_flag != 0;
-                if (run_epilogue) {
-                    // (2) last arriver: reduce all partials in fixed split order (deterministic), put the sum back into TMEM
-                    __threadfence();
-                    const float* base = p.sk_ws + ((size_t)unit_t * p.sk_splits * BM + rit) * BN;
+                run_epilogue = false;
+                if constexpr (EPI == EPI_RESID) {
+                    // (1) publish this unit's partial accumulator (fp32, [128][BN])
+                    const int rit = ew * 32 + lane;  // row in tile
+                    float* my = p.sk_ws + ((size_t)(unit_t * p.sk_splits + unit_s) * BM + rit) * BN;
 #pragma unroll 1
                     for (int c = 0; c < BN / 32; ++c) {
-                        float acc[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                        for (int sp = 0; sp < p.sk_splits; ++sp) {
-                            const float4* s4 = reinterpret_cast<const float4*>(base + (size_t)sp * BM * BN + c * 32);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 t = __ldcg(s4 + i);
-                                acc[4 * i] += t.x; acc[4 * i + 1] += t.y; acc[4 * i + 2] += t.z; acc[4 * i + 3] += t.w;
-                            }
-                        }
                         uint32_t v[32];
+                        tmem_ld_32x32b_x32(tbase + c * 32, v);
+                        tmem_ld_wait();
+                        uint4* d4 = reinterpret_cast<uint4*>(my + c * 32);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[i]);
-                        tmem_st_32x32b_x32(tbase + c * 32, v);
+                        for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
-                    tmem_st_wait();
+                    __threadfence();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps
+                    // (2) wait until every unit of this tile has published (all units are co-resident: one CTA per SM)
+                    if (ew == 0 && lane == 0) {
+                        atomicAdd(p.sk_cnt + 2 * unit_t, 1);
+                        uint32_t spins = 0;
+                        while (*reinterpret_cast<volatile int*>(p.sk_cnt + 2 * unit_t) < p.sk_splits) {
+                            if (++spins > (1u << 26)) { printf("mmdp: split-K wait timeout tile %d\n", unit_t); __trap(); }
+                        }
+                        __threadfence();
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    // (3) distributed reduction + residual epilogue: this unit owns 1/splits of the tile's float4 groups.
+                    //     Partials are summed in split order 0..S-1 (deterministic), then bf16(bf16(sum) + resid).
+                    const int groups = BM * BN / 4;
+                    const int per = (groups + p.sk_splits - 1) / p.sk_splits;
+                    const int g0 = unit_s * per, g1 = (g0 + per < groups) ? g0 + per : groups;
+                    const float* tbase_ws = p.sk_ws + (size_t)unit_t * p.sk_splits * BM * BN;
+                    const int tid = ew * 32 + lane;
+                    for (int g = g0 + tid; g < g1; g += 128) {
+                        const int rr = (g * 4) / BN, cc = (g * 4) - rr * BN;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int sp = 0; sp < p.sk_splits; ++sp) {
+                            const float4 t = __ldcg(reinterpret_cast<const float4*>(tbase_ws + ((size_t)sp * BM + rr) * BN + cc));
+                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                        }
+                        const int grow = m_blk * BM + rr, gcol = n_blk * BN + cc;
+                        if (grow < p.M && gcol < p.N) {
+                            const uint2 rv = *reinterpret_cast<const uint2*>(p.resid + (size_t)grow * p.ldr + gcol);
+                            uint2 o;
+                            o.x = pack_bf16x2(__fadd_rn(bf16_lo(rv.x), bf16_round(acc.x)), __fadd_rn(bf16_hi(rv.x), bf16_round(acc.y)));
+                            o.y = pack_bf16x2(__fadd_rn(bf16_lo(rv.y), bf16_round(acc.z)), __fadd_rn(bf16_hi(rv.y), bf16_round(acc.w)));
+                            *reinterpret_cast<uint2*>(p.C + (size_t)grow * p.ldc + gcol) = o;
+                        }
+                    }
+                    // (4) the last unit to finish re-arms the counters for the next launch
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (ew == 0 && lane == 0) {
+                        const int old = atomicAdd(p.sk_cnt + 2 * unit_t + 1, 1);
+                        if (old == p.sk_splits - 1) { p.sk_cnt[2 * unit_t] = 0; p.sk_cnt[2 * unit_t + 1] = 0; }
+                    }
                 }
             }
             if (run_epilogue) gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk);
@@ -269,7 +279,7 @@ static GemmPlan plan_gemm(int epi, int M, int N, int K) {
                 splits = (num_k + kb_per - 1) / kb_per;
                 pl.tail = tail; pl.splits = splits; pl.kb_per = kb_per;
                 pl.grid = full > 0 ? g : tail * splits;
-                waves = (double)(full / g) + (double)kb_per / num_k + 0.06;
+                waves = (double)(full / g) + (double)kb_per / num_k + 0.10;
             }
         }
         const double cost = waves * bn * (bn == 192 ? 1.04 : 1.0);
@@ -284,8 +294,8 @@ static int ensure_splitk_workspace() {
     if (g_sk_ws) return 0;
     const size_t units = 256;  // >= number of SMs
     MMDP_CUDA(cudaMalloc(&g_sk_ws, units * BM * 256 * sizeof(float)));
-    MMDP_CUDA(cudaMalloc(&g_sk_cnt, units * sizeof(int)));
-    MMDP_CUDA(cudaMemset(g_sk_cnt, 0, units * sizeof(int)));
+    MMDP_CUDA(cudaMalloc(&g_sk_cnt, 2 * units * sizeof(int)));  // [tile][arrived, finished]
+    MMDP_CUDA(cudaMemset(g_sk_cnt, 0, 2 * units * sizeof(int)));
     return 0;
 }
 
