@@ -146,6 +146,13 @@ MMDP_API int mmdp_vqdec_missing(mmdp_vqdec* d, char* out, int out_len);
 /* ids int64 [B, h*w] (device) -> pixels fp32 [B, out_ch, H, W] (device), H = h * 2^(n_levels-1). */
 MMDP_API int mmdp_vqdec_decode(mmdp_vqdec* d, const int64_t* ids, int B, int h, int w, float* out_nchw, void* stream);
 
+/* VQ encoder context: MAGVITv2.get_code (modeling_magvitv2.py:423-427). Same config struct (out_ch = image channels,
+ * latent_h/w = code grid => pixels = latent << (n_levels-1); ch_mult / num_res_blocks in ENCODER order (1,2,2,4,4)/(4,3,4,3,4));
+ * parameters are loaded with mmdp_vqdec_set_weight under the reference's 'encoder.*' names; destroy with mmdp_vqdec_destroy.
+ * pixels fp32 [B, 3, H, W] (device) -> ids int64 [B, (H/16)*(W/16)]. */
+MMDP_API int mmdp_vqenc_create(const mmdp_vqdec_config* cfg, mmdp_vqdec** out);
+MMDP_API int mmdp_vqenc_encode(mmdp_vqdec* enc, const float* pixels_nchw, int B, int H, int W, int64_t* ids_out, void* stream);
+
 /* ---- whole-model context (LLaDAModel.forward, modeling_llada.py:1201-1415) ----------------------------------- */
 typedef struct mmdp_model mmdp_model;
 

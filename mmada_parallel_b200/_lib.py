@@ -82,6 +82,8 @@ SIGNATURES = {
     "mmdp_vqdec_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "mmdp_vqdec_missing": (_i, [_vp, C.c_char_p, _i]),
     "mmdp_vqdec_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mmdp_vqenc_create": (_i, [C.POINTER(VqDecConfig), C.POINTER(_vp)]),
+    "mmdp_vqenc_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "mmdp_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "mmdp_model_destroy": (None, [_vp]),
     "mmdp_model_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i64, _vp]),

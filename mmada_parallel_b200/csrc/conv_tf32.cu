@@ -344,6 +344,69 @@ __global__ void padded_to_nchw_kernel(const float* __restrict__ x, float* __rest
     }
 }
 
+// ---- encoder-side row kernels (MAGVITv2.get_code) ---------------------------------------------------------------
+// NCHW pixels [B, C, H, W] -> padded channels-last [B, (H+2)(W+2), Cpad] (extra channels and the border are zero)
+__global__ void __launch_bounds__(256) nchw_to_padded_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cpad, int H, int W) {
+    const int b = blockIdx.y, Wp = W + 2, Hp = H + 2;
+    const long long n = (long long)Hp * Wp * Cpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cpad);
+        const long long pix = i / Cpad;
+        const int yy = (int)(pix / Wp), xx = (int)(pix - (long long)yy * Wp);
+        float v = 0.f;
+        if (c < C && yy >= 1 && yy <= H && xx >= 1 && xx <= W) v = x[(((size_t)b * C + c) * H + (yy - 1)) * W + (xx - 1)];
+        y[(size_t)b * n + i] = v;
+    }
+}
+// Downsample (common_modules.py:73-90): pad (0,1,0,1) + 3x3 stride-2 conv == the stride-1 zero-border conv evaluated at
+// input pixel (2y+1, 2x+1). src: padded [B, (H+2)(W+2), C] holding the stride-1 result; dst: padded [B, (H/2+2)(W/2+2), C].
+__global__ void __launch_bounds__(256) downsample_pick_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
+    const int b = blockIdx.y, Wp = W + 2, H2 = H / 2, W2 = W / 2, Wp2 = W2 + 2, Hp2 = H2 + 2, C4 = C / 4;
+    const long long n = (long long)Hp2 * Wp2 * C4;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const long long pix = i / C4;
+        const int yy = (int)(pix / Wp2), xx = (int)(pix - (long long)yy * Wp2);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 1 && yy <= H2 && xx >= 1 && xx <= W2)
+            v = s4[((size_t)b * (H + 2) * Wp + (size_t)(2 * (yy - 1) + 2) * Wp + (2 * (xx - 1) + 2)) * C4 + c];
+        d4[(size_t)b * n + i] = v;
+    }
+}
+// LFQ sign quantisation + get_indices (modeling_magvitv2.py:201-206): padded [B, (h+2)(w+2), ld] -> int64 ids [B, h*w]
+__global__ void lfq_indices_kernel(const float* __restrict__ z, int64_t* __restrict__ ids, int h, int w, int bits, int ld) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= h * w) return;
+    const int y = n / w, x = n - y * w;
+    const float* src = z + ((size_t)b * (h + 2) * (w + 2) + (size_t)(y + 1) * (w + 2) + x + 1) * ld;
+    int64_t id = 0;
+    for (int c = 0; c < bits; ++c) id |= (int64_t)(src[c] > 0.f) << (bits - 1 - c);
+    ids[(size_t)b * h * w + n] = id;
+}
+
+int nchw_to_padded(const float* x, float* y, int B, int C, int Cpad, int H, int W, cudaStream_t stream) {
+    LaunchScope ls(LK_ROW, (double)B * H * W * (C + Cpad) * 4, stream);
+    nchw_to_padded_kernel<<<dim3(148 * 4, B), 256, 0, stream>>>(x, y, C, Cpad, H, W);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+int downsample_pick(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t stream) {
+    if ((C % 4) || (H % 2) || (W % 2)) return set_error("downsample: C %% 4 and even H, W required");
+    LaunchScope ls(LK_ROW, (double)B * (H / 2) * (W / 2) * C * 8, stream);
+    downsample_pick_kernel<<<dim3(148 * 4, B), 256, 0, stream>>>(src, dst, C, H, W);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+int lfq_indices(const float* z, int64_t* ids, int B, int h, int w, int bits, int ld, cudaStream_t stream) {
+    LaunchScope ls(LK_ROW, (double)B * h * w * (bits * 4 + 8), stream);
+    lfq_indices_kernel<<<dim3((h * w + 255) / 256, B), 256, 0, stream>>>(z, ids, h, w, bits, ld);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int gn_swish(const float* x, float* y, int B, int C, int H, int W, double* stats_ws, const float* gamma, const float* beta,
              float eps, int swish, int compact, cudaStream_t stream) {
     if (C % 32) return set_error("group_norm: channels must be a multiple of 32");

@@ -52,6 +52,9 @@ int upsample2x(const float* x, float* y, int B, int C, int H, int W, cudaStream_
 int softmax_rows_ld(float* s, int rows, int n, int ld, cudaStream_t stream);
 int zero_border(float* y, int B, int C, int H, int W, cudaStream_t stream);
 int lfq_to_padded(const int64_t* ids, float* z, int B, int H, int W, int bits, int Cpad, cudaStream_t stream);
+int nchw_to_padded(const float* x, float* y, int B, int C, int Cpad, int H, int W, cudaStream_t stream);
+int downsample_pick(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t stream);
+int lfq_indices(const float* z, int64_t* ids, int B, int h, int w, int bits, int ld, cudaStream_t stream);
 int padded_to_nchw(const float* x, float* y, int B, int C, int ld, int H, int W, cudaStream_t stream);
 
 struct QkvRopeArgs {

@@ -332,3 +332,112 @@ extern "C" MMDP_API int mmdp_vqdec_decode(mmdp_vqdec* d, const int64_t* ids, int
     if (f.conv("decoder.conv_out", T, H, W, Y, nullptr)) return -1;
     return padded_to_nchw(Y, out_nchw, B, c.out_ch, round32(c.out_ch), H, W, s);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Encoder: MAGVITv2.get_code (modeling_magvitv2.py:423-427) = VQGANEncoder.forward (:143-169) + LFQ sign bits.
+// Same net object type as the decoder (weights registry + rotating activation buffers); parameters are registered
+// under the reference's 'encoder.*' names. Downsample (3x3, stride 2, pad (0,1,0,1)) = the stride-1 zero-border conv
+// followed by picking input pixels (2y+1, 2x+1).
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+MMDP_API int mmdp_vqenc_create(const mmdp_vqdec_config* c, mmdp_vqdec** out) {
+    if (!c || !out) return set_error("mmdp_vqenc_create: null argument");
+    if (c->n_levels < 1 || c->n_levels > 8 || c->ch % 32 || c->z_channels < 1 || c->z_channels > 32 || c->out_ch < 1 ||
+        c->out_ch > 32 || c->max_batch < 1 || c->latent_h < 1 || c->latent_w < 1)
+        return set_error("mmdp_vqenc_create: bad config (out_ch = image channels; latent_h/w = code grid)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_error("mmdp_vqenc_create: no CUDA device (this library has no CPU fallback)");
+    mmdp_vqdec* d = new mmdp_vqdec();
+    d->cfg = *c;
+    const int nres = c->n_levels;
+    int rc = 0;
+    int H = c->latent_h << (nres - 1), W = c->latent_w << (nres - 1);  // pixel resolution
+    rc |= add_conv(d, "encoder.conv_in", c->ch, c->out_ch, 3);
+    size_t max_elems = (size_t)(H + 2) * (W + 2) * c->ch;
+    int block_in = c->ch;
+    for (int lvl = 0; lvl < nres; ++lvl) {
+        const int block_out = c->ch * c->ch_mult[lvl];
+        for (int b = 0; b < c->num_res_blocks[lvl]; ++b) {
+            rc |= add_resblock(d, "encoder.down." + std::to_string(lvl) + ".block." + std::to_string(b), block_in, block_out);
+            const size_t e = (size_t)(H + 2) * (W + 2) * (block_in > block_out ? block_in : block_out);
+            if (e > max_elems) max_elems = e;
+            block_in = block_out;
+        }
+        if (lvl != nres - 1) {
+            rc |= add_conv(d, "encoder.down." + std::to_string(lvl) + ".downsample.conv", block_in, block_in, 3);
+            H /= 2; W /= 2;
+        }
+    }
+    rc |= add_resblock(d, "encoder.mid.block_1", block_in, block_in);
+    rc |= add_norm(d, "encoder.mid.attn_1.norm", block_in);
+    for (const char* n : {"q", "k", "v", "proj_out"}) rc |= add_conv(d, std::string("encoder.mid.attn_1.") + n, block_in, block_in, 1);
+    rc |= add_resblock(d, "encoder.mid.block_2", block_in, block_in);
+    rc |= add_norm(d, "encoder.norm_out", block_in);
+    rc |= add_conv(d, "encoder.conv_out", c->z_channels, block_in, 3);
+    rc |= add_conv(d, "encoder.quant_conv", c->z_channels, c->z_channels, 1);
+    d->buf_elems = max_elems * c->max_batch;
+    for (int i = 0; i < 4; ++i) rc |= vq_alloc(d, (void**)&d->buf[i], d->buf_elems * 4);
+    const size_t hw = (size_t)c->latent_h * c->latent_w;
+    const int cm = block_in;
+    rc |= vq_alloc(d, (void**)&d->q, (size_t)c->max_batch * hw * cm * 4);
+    rc |= vq_alloc(d, (void**)&d->k, (size_t)c->max_batch * hw * cm * 4);
+    rc |= vq_alloc(d, (void**)&d->o, (size_t)c->max_batch * hw * cm * 4);
+    rc |= vq_alloc(d, (void**)&d->vt, (size_t)cm * round32((int)hw) * 4);
+    rc |= vq_alloc(d, (void**)&d->s, hw * round32((int)hw) * 4);
+    rc |= vq_alloc(d, (void**)&d->stats, (size_t)c->max_batch * 32 * 2 * sizeof(double));
+    rc |= vq_alloc(d, (void**)&d->stage, d->stage_elems * 4);
+    if (rc) {
+        mmdp_vqdec_destroy(d);
+        return -1;
+    }
+    *out = d;
+    return 0;
+}
+
+MMDP_API int mmdp_vqenc_encode(mmdp_vqdec* d, const float* pixels_nchw, int B, int H, int W, int64_t* ids_out, void* stream) {
+    if (!d || !pixels_nchw || !ids_out) return set_error("mmdp_vqenc_encode: null argument");
+    const mmdp_vqdec_config& c = d->cfg;
+    const int nres = c.n_levels;
+    if (B < 1 || B > c.max_batch || H != (c.latent_h << (nres - 1)) || W != (c.latent_w << (nres - 1)))
+        return set_error("mmdp_vqenc_encode: B=%d H=%d W=%d outside the context (max_batch=%d, %dx%d pixels)", B, H, W, c.max_batch,
+                         c.latent_h << (nres - 1), c.latent_w << (nres - 1));
+    if (!d->conv.count("encoder.conv_in")) return set_error("mmdp_vqenc_encode: not an encoder context");
+    char miss[256];
+    if (mmdp_vqdec_missing(d, miss, sizeof(miss)) != 0) return set_error("mmdp_vqenc_encode: parameters not loaded: %s", miss);
+    cudaStream_t s = (cudaStream_t)stream;
+    Fwd f{d, s, B};
+    const int cin = round32(c.out_ch);
+    if (nchw_to_padded(pixels_nchw, d->buf[0], B, c.out_ch, cin, H, W, s)) return -1;
+    if (f.conv("encoder.conv_in", d->buf[0], H, W, d->buf[1], nullptr)) return -1;
+    int ix = 1;
+    for (int lvl = 0; lvl < nres; ++lvl) {
+        for (int b = 0; b < c.num_res_blocks[lvl]; ++b)
+            if (f.resblock("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(b), H, W, ix)) return -1;
+        if (lvl != nres - 1) {
+            const int C = c.ch * c.ch_mult[lvl];
+            float* X = d->buf[ix];
+            float* T = d->buf[(ix + 1) & 3];
+            float* Y = d->buf[(ix + 3) & 3];
+            if (f.conv("encoder.down." + std::to_string(lvl) + ".downsample.conv", X, H, W, T, nullptr)) return -1;
+            if (downsample_pick(T, Y, B, C, H, W, s)) return -1;
+            H /= 2; W /= 2;
+            ix = (ix + 3) & 3;
+        }
+    }
+    if (f.resblock("encoder.mid.block_1", H, W, ix)) return -1;
+    if (f.attn("encoder.mid.attn_1", H, W, ix)) return -1;
+    if (f.resblock("encoder.mid.block_2", H, W, ix)) return -1;
+    float* X = d->buf[ix];
+    float* T = d->buf[(ix + 1) & 3];
+    float* Y = d->buf[(ix + 3) & 3];
+    if (f.gn("encoder.norm_out", X, T, H, W, 1, 0)) return -1;
+    const int zc = round32(c.z_channels);
+    MMDP_CUDA(cudaMemsetAsync(Y, 0, (size_t)B * (H + 2) * (W + 2) * zc * 4, s));  // channels z..31 stay zero (quant_conv input)
+    if (f.conv("encoder.conv_out", T, H, W, Y, nullptr)) return -1;
+    if (f.conv("encoder.quant_conv", Y, H, W, X, nullptr)) return -1;
+    return lfq_indices(X, ids_out, B, H, W, c.z_channels, zc, s);
+}
+
+}  // extern "C"

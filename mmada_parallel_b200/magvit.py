@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 from types import SimpleNamespace
-from typing import Dict, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -72,15 +72,79 @@ class VQGANDecoder:
         return out
 
 
-class MAGVITv2:
-    """Inference-side mirror of the reference class: `decode_code(ids[B, N], shape=None) -> FloatTensor[B, 3, H, W]`."""
+class VQGANEncoder:
+    """Encoder half (modeling_magvitv2.py:62-169): pixels [B, 3, H, W] -> 13-channel pre-quantisation map; `encode_ids`
+    returns the LFQ code indices (MAGVITv2.get_code, :423-427) in one C call."""
 
-    def __init__(self, max_batch: int = 1, device: str = "cuda:0", **decoder_kw):
+    def __init__(self, ch: int = 128, ch_mult: Sequence[int] = (1, 2, 2, 4, 4), num_res_blocks: Sequence[int] = (4, 3, 4, 3, 4),
+                 z_channels: int = 13, in_ch: int = 3, latent_hw=(32, 32), max_batch: int = 1, device: str = "cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.MmdpError("mmada_parallel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        c = _lib.VqDecConfig()
+        c.ch, c.n_levels, c.z_channels, c.out_ch, c.max_batch = ch, len(ch_mult), z_channels, in_ch, max_batch
+        c.latent_h, c.latent_w = latent_hw
+        for i, (m, n) in enumerate(zip(ch_mult, num_res_blocks)):
+            c.ch_mult[i], c.num_res_blocks[i] = m, n
+        h = C.c_void_p()
+        check(lib.mmdp_vqenc_create(C.byref(c), C.byref(h)))
+        self._h = h
+        self.downscale = 2 ** (len(ch_mult) - 1)
+        self.in_ch = in_ch
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            lib.mmdp_vqdec_destroy(h)
+            self._h = None
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        unexpected = []
+        for k, v in state_dict.items():
+            if k.startswith("decoder.") or k.startswith("quantize."):
+                continue
+            name = k if k.startswith("encoder.") else "encoder." + k
+            t = v.detach().to(torch.float32).contiguous()
+            if lib.mmdp_vqdec_set_weight(self._h, name.encode(), t.data_ptr(), t.numel(), stream_ptr()) != 0:
+                unexpected.append(k)
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(512)
+        missing = lib.mmdp_vqdec_missing(self._h, buf, 512)
+        if strict and (missing or unexpected):
+            raise KeyError(f"VQGANEncoder.load_state_dict: {missing} missing ({buf.value.decode()[:200]}), unexpected={unexpected[:6]}")
+        return SimpleNamespace(missing_keys=buf.value.decode().split(), unexpected_keys=unexpected)
+
+    def encode_ids(self, pixels: torch.Tensor) -> torch.Tensor:
+        x = pixels.to(device=self.device, dtype=torch.float32).contiguous()
+        b, c, hh, ww = x.shape
+        if c != self.in_ch or hh % self.downscale or ww % self.downscale:
+            raise ValueError(f"get_code: expected [B, {self.in_ch}, H, W] with H, W multiples of {self.downscale}")
+        ids = torch.empty((b, (hh // self.downscale) * (ww // self.downscale)), dtype=torch.int64, device=self.device)
+        check(lib.mmdp_vqenc_encode(self._h, ptr(x), b, hh, ww, ptr(ids), stream_ptr()))
+        return ids
+
+
+class MAGVITv2:
+    """Inference-side mirror of the reference class: `decode_code(ids[B, N], shape=None) -> FloatTensor[B, 3, H, W]` and
+    `get_code(pixels[B, 3, H, W]) -> LongTensor[B, N]`. The encoder context is created on first use (encoder weights in
+    the state dict, or the first get_code call)."""
+
+    def __init__(self, max_batch: int = 1, device: str = "cuda:0", encoder_kw: Optional[dict] = None, **decoder_kw):
         self.decoder = VQGANDecoder(max_batch=max_batch, device=device, **decoder_kw)
         self.device = self.decoder.device
+        self._enc_kw = dict(max_batch=max_batch, device=device, latent_hw=self.decoder.cfg.latent_hw, **(encoder_kw or {}))
+        self.encoder: Optional[VQGANEncoder] = None
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        return self.decoder.load_state_dict(state_dict, strict=strict)
+        res = None
+        if any(k.startswith("decoder.") for k in state_dict) or not any(k.startswith("encoder.") for k in state_dict):
+            res = self.decoder.load_state_dict(state_dict, strict=strict)
+        if any(k.startswith("encoder.") for k in state_dict):
+            if self.encoder is None:
+                self.encoder = VQGANEncoder(**self._enc_kw)
+            res = self.encoder.load_state_dict(state_dict, strict=strict)
+        return res
 
     def eval(self):
         return self
@@ -92,5 +156,8 @@ class MAGVITv2:
     def decode_code(self, codebook_indices: torch.Tensor, shape=None) -> torch.Tensor:
         return self.decoder.decode_ids(codebook_indices, shape=shape)
 
-    def get_code(self, pixel_values):
-        raise NotImplementedError("VQ encode (MAGVITv2.get_code, :423-427) is the next row of the scope table (SURVEY.md 8f rank 1)")
+    @torch.no_grad()
+    def get_code(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        if self.encoder is None:
+            raise _lib.MmdpError("MAGVITv2.get_code: encoder weights were not loaded (state dict had no 'encoder.*' entries)")
+        return self.encoder.encode_ids(pixel_values)

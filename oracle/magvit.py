@@ -143,3 +143,97 @@ def decode_code(indices: torch.Tensor, w: Dict[str, torch.Tensor], cfg, shape=No
         hh, ww = shape
     z_q = lfq_codebook_entry(indices, cfg.z_channels).view(b, cfg.z_channels, hh, ww)
     return decoder_forward(z_q, w, cfg)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# encoder side: MAGVITv2.get_code (modeling_magvitv2.py:423-427) = VQGANEncoder.forward (:143-169) + LFQ sign bits
+# ---------------------------------------------------------------------------------------------------------------
+def encoder_config(ch=128, ch_mult=(1, 2, 2, 4, 4), num_res_blocks=(4, 3, 4, 3, 4), z_channels=13, in_ch=3):
+    """Defaults of VQGANEncoder.__init__ (modeling_magvitv2.py:62-73)."""
+    return SimpleNamespace(ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=tuple(num_res_blocks), z_channels=z_channels, in_ch=in_ch)
+
+
+def encoder_param_shapes(cfg) -> Dict[str, tuple]:
+    sh: Dict[str, tuple] = {}
+
+    def conv(name, cout, cin, k):
+        sh[name + ".weight"] = (cout, cin, k, k)
+        sh[name + ".bias"] = (cout,)
+
+    def norm(name, c):
+        sh[name + ".weight"] = (c,)
+        sh[name + ".bias"] = (c,)
+
+    def resblock(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cout, cin, 3)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".nin_shortcut", cout, cin, 1)
+
+    conv("encoder.conv_in", cfg.ch, cfg.in_ch, 3)
+    in_ch_mult = (1,) + tuple(cfg.ch_mult)
+    nres = len(cfg.ch_mult)
+    block_in = cfg.ch
+    for i_level in range(nres):
+        block_in = cfg.ch * in_ch_mult[i_level]
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        for i_block in range(cfg.num_res_blocks[i_level]):
+            resblock(f"encoder.down.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != nres - 1:
+            conv(f"encoder.down.{i_level}.downsample.conv", block_in, block_in, 3)
+    resblock("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv("encoder.mid.attn_1." + n, block_in, block_in, 1)
+    resblock("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", cfg.z_channels, block_in, 3)
+    conv("encoder.quant_conv", cfg.z_channels, cfg.z_channels, 1)
+    return sh
+
+
+def make_encoder_weights(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in encoder_param_shapes(cfg).items():
+        if name.endswith(".weight") and len(shape) == 4:
+            sd[name] = torch.randn(shape, generator=g) * (1.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+        elif len(shape) == 1 and ".norm" in name and name.endswith(".weight"):
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+    return sd
+
+
+@torch.no_grad()
+def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg) -> torch.Tensor:
+    """VQGANEncoder.forward (modeling_magvitv2.py:143-169): pixels [B, 3, H, W] -> pre-quantisation z [B, 13, H/16, W/16]."""
+    nres = len(cfg.ch_mult)
+    h = _conv(x, w, "encoder.conv_in", 1)
+    for i_level in range(nres):
+        for i_block in range(cfg.num_res_blocks[i_level]):
+            h = _resblock(h, w, f"encoder.down.{i_level}.block.{i_block}")
+        if i_level != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)                 # Downsample, common_modules.py:83-87
+            h = F.conv2d(h, w[f"encoder.down.{i_level}.downsample.conv.weight"], w[f"encoder.down.{i_level}.downsample.conv.bias"],
+                         stride=2, padding=0)
+    h = _resblock(h, w, "encoder.mid.block_1")
+    h = _attn(h, w, "encoder.mid.attn_1")
+    h = _resblock(h, w, "encoder.mid.block_2")
+    h = nonlinearity(_norm(h, w, "encoder.norm_out"))
+    h = _conv(h, w, "encoder.conv_out", 1)
+    return _conv(h, w, "encoder.quant_conv", 0)
+
+
+def lfq_indices(z: torch.Tensor, bits: int = 13) -> torch.Tensor:
+    """LFQuantizer.forward sign quantisation + get_indices (modeling_magvitv2.py:201-206,238-241): [B, 13, h, w] -> int64 [B, h*w]."""
+    power = 2 ** torch.arange(bits - 1, -1, -1)
+    return (power.reshape(1, -1, 1, 1) * (z > 0).long()).sum(1).reshape(z.shape[0], -1)
+
+
+@torch.no_grad()
+def get_code(pixels: torch.Tensor, w: Dict[str, torch.Tensor], cfg) -> torch.Tensor:
+    return lfq_indices(encoder_forward(pixels, w, cfg), cfg.z_channels)

@@ -39,6 +39,28 @@ def main():
         print(tag, "ok", tuple(ref.shape), "std", float(ref.std()), "absmax", float(ref.abs().max()))
     torch.save(out, os.path.join(OUT, "magvit_decode.pt"))
 
+    # ---- encoder: MAGVITv2.get_code -------------------------------------------------------------------------
+    enc_out = {}
+    small_e = magvit.encoder_config(ch=32, ch_mult=(1, 2), num_res_blocks=(1, 2))
+    full_e = magvit.encoder_config()
+    for tag, cfg, seed, res, batch in (("small", small_e, 13, 32, 2), ("full", full_e, 14, 512, 1)):
+        w = magvit.make_encoder_weights(cfg, seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            enc = mv.VQGANEncoder(ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=list(cfg.num_res_blocks), z_channels=cfg.z_channels).eval()
+            lfq = mv.LFQuantizer(codebook_dim=13)
+        enc.load_state_dict({k[len("encoder."):]: v for k, v in w.items()}, strict=True)
+        px = torch.rand(batch, 3, res, res, generator=torch.Generator().manual_seed(seed + 100)) * 2 - 1
+        with torch.no_grad():
+            z_ref = enc(px)
+            ids_ref = lfq.get_indices(lfq(z_ref)["z"]).reshape(batch, -1)          # == MAGVITv2.get_code
+        z = magvit.encoder_forward(px, w, cfg)
+        assert torch.equal(z_ref, z), f"oracle encoder != reference encoder ({tag})"
+        assert torch.equal(ids_ref, magvit.get_code(px, w, cfg)), f"oracle get_code != reference ({tag})"
+        enc_out[tag] = dict(cfg=dict(ch=cfg.ch, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks), weight_seed=seed,
+                            pixel_seed=seed + 100, res=res, batch=batch, z=z_ref.clone(), ids=ids_ref.clone())
+        print("encoder", tag, "ok", tuple(z_ref.shape), "z std", float(z_ref.std()))
+    torch.save(enc_out, os.path.join(OUT, "magvit_encode.pt"))
+
 
 if __name__ == "__main__":
     main()
