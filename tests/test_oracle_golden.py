@@ -126,3 +126,18 @@ def test_magvit_decoder_matches_reference_golden():
     assert torch.equal(out[:, :, ::g["stride"], ::g["stride"]], g["image"])
     names = OM.param_shapes(OM.decoder_config())
     assert sum(torch.Size(s).numel() for s in names.values()) > 39_000_000  # the real decoder (~39.9 M parameters)
+
+
+def test_magvit_encoder_matches_reference_golden():
+    from oracle import magvit as OM
+    g = load_golden("magvit_encode.pt")["small"]
+    cfg = OM.encoder_config(**g["cfg"])
+    w = OM.make_encoder_weights(cfg, g["weight_seed"])
+    px = torch.rand(g["batch"], 3, g["res"], g["res"], generator=torch.Generator().manual_seed(g["pixel_seed"])) * 2 - 1
+    assert torch.equal(OM.encoder_forward(px, w, cfg), g["z"])
+    assert torch.equal(OM.get_code(px, w, cfg), g["ids"])
+    # decode(get_code(x)) round trip stays on the code grid: ids -> +-1 bits -> ids (idempotence of the LFQ codebook)
+    from oracle.sampling import lfq_codebook_entry
+    ids = g["ids"]
+    side = int(ids.shape[1] ** 0.5)
+    assert torch.equal(OM.lfq_indices(lfq_codebook_entry(ids, 13).view(ids.shape[0], 13, side, side), 13), ids)
