@@ -43,7 +43,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    volatile int* sk_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;

@@ -17,7 +17,6 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
     f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
-__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 
 // ------------------------------------------------------------------------------------------------
 // text step, kernel 1: per-row argmax (first index on ties), fp64 softmax confidence of the argmax token

@@ -35,7 +35,6 @@ struct mmdp_vqdec {
     double* stats = nullptr;
     float* stage = nullptr;  // raw-weight staging for packing
     size_t stage_elems = 0;
-    int max_hw = 0;
 };
 
 static int round32(int c) { return (c + 31) / 32 * 32; }
