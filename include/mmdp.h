@@ -44,6 +44,8 @@ MMDP_API long long mmdp_launch_count(int reset);
 /* Kernel selection for large GEMMs: 0 = one CTA per 128xN tile (cta_group::1), 1 = CTA pair per 256xN tile (cta_group::2).
  * Results are bit-identical (same K order); also settable with the environment variable MMDP_GEMM_PAIR. */
 MMDP_API void mmdp_set_gemm_pair(int on);
+/* Attention kernel: 4 = O accumulated in TMEM with lazy rescale, two CTAs per SM (default); 3 = O in registers (MMDP_ATTN=3). */
+MMDP_API void mmdp_set_attention_version(int v);
 
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */
 #define MMDP_EPI_PLAIN 0   /* C = bf16(A W^T)                                 nn.Linear, modeling_llada.py:1402      */

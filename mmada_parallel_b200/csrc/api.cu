@@ -150,6 +150,7 @@ MMDP_API void mmdp_prof_enable(int on) { prof_enable(on); }
 MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches) { return prof_summary(ms, work, launches); }
 MMDP_API long long mmdp_launch_count(int reset) { return launch_count(reset); }
 MMDP_API void mmdp_set_gemm_pair(int on) { set_gemm_pair_mode(on); }
+MMDP_API void mmdp_set_attention_version(int v) { set_attention_version(v); }
 
 // ------------------------------------------------------------------------------------------------
 // model context

@@ -46,7 +46,7 @@ __device__ __forceinline__ void softmax_group_sync() {  // the 256 softmax threa
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
                  float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
@@ -314,7 +314,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
 }
 
-int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+int attention_fwd_v3(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                   int H, int L, int Lpad, float scale, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || L <= 0) return set_error("attention: empty problem");
     if (Lpad < L || (Lpad % 8)) return set_error("attention: Lpad must be >= L and a multiple of 8");
@@ -325,13 +325,13 @@ int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfl
     if (make_tmap_2d_bf16(&tmVt, vt, (uint64_t)B * H * 128, (uint64_t)Lpad, (uint64_t)Lpad, 128, 64)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
-        MMDP_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        MMDP_CUDA(cudaFuncSetAttribute(attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         attr_set = true;
     }
     dim3 grid((L + 127) / 128, H, B);
     const float scale_log2 = scale * 1.4426950408889634f;
     LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)L * L * 128, stream);
-    attention_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
+    attention_v3_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }

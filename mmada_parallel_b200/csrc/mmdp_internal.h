@@ -76,6 +76,8 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
 int gemm_pair_mode();
 void set_gemm_pair_mode(int on);
 
+// attention kernel selection: 4 (default, attention4.cu) or 3 (attention.cu); also MMDP_ATTN=3
+void set_attention_version(int v);
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                   int H, int L, int Lpad, float scale, cudaStream_t stream);
 
