@@ -24,7 +24,9 @@ static constexpr int k4QBytes = 128 * 128 * 2;       // 32 KB (two 64-column hal
 static constexpr int k4KBytes = k4BKV * 128 * 2;     // 16 KB (two halves of 64 rows x 64 cols)
 static constexpr int k4VBytes = 128 * k4BKV * 2;     // 16 KB (128 d rows x 64 kv)
 static constexpr int k4PBytes = 128 * k4BKV * 2;     // 16 KB
-static constexpr int k4Smem = k4QBytes + k4KBytes + k4VBytes + 2 * k4PBytes + 1024 + 256;
+// smem: Q | K[2] | V[2] | P | barriers = 112.25 KB; no alignment slack (the dynamic smem window of a kernel without static
+// smem starts 1024-aligned; checked at run time) so that two CTAs fit into the 227 KB of an SM
+static constexpr int k4Smem = k4QBytes + 2 * k4KBytes + 2 * k4VBytes + k4PBytes + 256;
 
 __device__ __forceinline__ float ex2_approx4(float x) {
     float y;
@@ -45,23 +47,27 @@ __global__ void __launch_bounds__(k4Threads, 2)
 attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
                     float scale_log2) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+        printf("mmdp: attention smem base not 1024-byte aligned\n");
+        __trap();
+    }
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + k4QBytes;
-    uint8_t* sV = sK + k4KBytes;
-    uint8_t* sP = sV + k4VBytes;  // 2 buffers
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * k4PBytes);
+    uint8_t* sK = sQ + k4QBytes;      // 2 stages
+    uint8_t* sV = sK + 2 * k4KBytes;  // 2 stages
+    uint8_t* sP = sV + 2 * k4VBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + k4PBytes);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;
-    uint64_t* k_empty = bars + 2;
-    uint64_t* v_full = bars + 3;
-    uint64_t* v_empty = bars + 4;
-    uint64_t* s_full = bars + 5;   // [2]
-    uint64_t* s_empty = bars + 7;  // [2]
-    uint64_t* p_full = bars + 9;   // [2]
-    uint64_t* pv_done = bars + 11;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;    // [2]
+    uint64_t* s_empty = bars + 11;  // [2]
+    uint64_t* p_full = bars + 13;
+    uint64_t* pv_done = bars + 14;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -69,15 +75,15 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     if (warp == 5 && lane == 0) {
         mbar_init(q_full, 1);
-        mbar_init(k_full, 1);
-        mbar_init(k_empty, 1);
-        mbar_init(v_full, 1);
-        mbar_init(v_empty, 1);
         for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], 4);
-            mbar_init(&p_full[s], 4);
         }
+        mbar_init(p_full, 4);
         mbar_init(pv_done, 1);
         fence_barrier_init();
     }
@@ -104,15 +110,16 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tma_load_2d(sQ, &tmQ, q_full, h * 128, qrow0);
             tma_load_2d(sQ + k4QBytes / 2, &tmQ, q_full, h * 128 + 64, qrow0);
             for (int j = 0; j < n_kv; ++j) {
-                const uint32_t u = j & 1;
+                const int st = j & 1;
+                const uint32_t u = (j >> 1) & 1;
                 const int kv0 = j * k4BKV;
-                mbar_wait(k_empty, u ^ 1);
-                mbar_expect_tx(k_full, k4KBytes);
-                tma_load_2d(sK, &tmK, k_full, h * 128, b * L + kv0);
-                tma_load_2d(sK + k4KBytes / 2, &tmK, k_full, h * 128 + 64, b * L + kv0);
-                mbar_wait(v_empty, u ^ 1);
-                mbar_expect_tx(v_full, k4VBytes);
-                tma_load_2d(sV, &tmVt, v_full, kv0, (b * H + h) * 128);
+                mbar_wait(&k_empty[st], u ^ 1);
+                mbar_expect_tx(&k_full[st], k4KBytes);
+                tma_load_2d(sK + st * k4KBytes, &tmK, &k_full[st], h * 128, b * L + kv0);
+                tma_load_2d(sK + st * k4KBytes + k4KBytes / 2, &tmK, &k_full[st], h * 128 + 64, b * L + kv0);
+                mbar_wait(&v_empty[st], u ^ 1);
+                mbar_expect_tx(&v_full[st], k4VBytes);
+                tma_load_2d(sV + st * k4VBytes, &tmVt, &v_full[st], kv0, (b * H + h) * 128);
             }
         }
         __syncwarp();
@@ -121,13 +128,15 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) {
             constexpr uint32_t idesc_qk = umma_idesc_bf16(128, k4BKV);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128);
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+            const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
             mbar_wait(q_full, 0);
             for (int j = 0; j <= n_kv; ++j) {
                 if (j < n_kv) {
                     const int s = j & 1;
-                    mbar_wait(k_full, j & 1);
-                    mbar_wait(&s_empty[s], ((j >> 1) & 1) ^ 1);
+                    const uint32_t u = (j >> 1) & 1;
+                    const uint32_t aK = smem_u32(sK + s * k4KBytes);
+                    mbar_wait(&k_full[s], u);
+                    mbar_wait(&s_empty[s], u ^ 1);
                     tcgen05_fence_after();
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {  // K dimension = head_dim 128: two 64-column halves of Q and K
@@ -135,19 +144,19 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         umma_bf16_ss(tS0 + s * k4BKV, umma_desc_kmajor_sw128(aQ + qoff) + (k & 3) * 2,
                                      umma_desc_kmajor_sw128(aK + koff) + (k & 3) * 2, idesc_qk, k != 0);
                     }
-                    umma_commit(k_empty);
+                    umma_commit(&k_empty[s]);
                     umma_commit(&s_full[s]);
                 }
                 if (j >= 1) {
                     const int jj = j - 1, s = jj & 1;
-                    mbar_wait(v_full, jj & 1);
-                    mbar_wait(&p_full[s], (jj >> 1) & 1);
+                    const uint32_t aV = smem_u32(sV + s * k4VBytes);
+                    mbar_wait(&v_full[s], (jj >> 1) & 1);
+                    mbar_wait(p_full, jj & 1);
                     tcgen05_fence_after();
 #pragma unroll
                     for (int k = 0; k < k4BKV / 16; ++k)  // K dimension = 64 kv of this block
-                        umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP + s * k4PBytes) + k * 2, umma_desc_kmajor_sw128(aV) + k * 2,
-                                     idesc_pv, (jj | k) != 0);
-                    umma_commit(v_empty);
+                        umma_bf16_ss(tO, umma_desc_kmajor_sw128(aP) + k * 2, umma_desc_kmajor_sw128(aV) + k * 2, idesc_pv, (jj | k) != 0);
+                    umma_commit(&v_empty[s]);
                     umma_commit(pv_done);
                 }
             }
@@ -184,14 +193,32 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(sv[i]));
             const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
 
-            // lazy rescale: only when this row's max exceeds the max in use by more than 2^kLazy (always on the first block)
+            // lazy rescale decision: only when this row's max exceeds the max in use by more than 2^kLazy (always on block 0)
             const bool need = (mx - m_used) * scale_log2 > kLazy;  // m_used = -inf on block 0 -> true
-            if (__any_sync(0xffffffffu, need)) {
-                const float m_new = need ? mx : m_used;
-                const float alpha = need ? ex2_approx4((m_used - m_new) * scale_log2) : 1.0f;  // 0 on the first block
-                if (j >= 1) {
-                    mbar_wait(pv_done, (j - 1) & 1);  // O holds PV(0..j-1); PV(j) is not issued before p_full(j)
-                    tcgen05_fence_after();
+            const bool any_need = __any_sync(0xffffffffu, need);
+            const float m_new = need ? mx : m_used;
+            const float alpha = need ? ex2_approx4((m_used - m_new) * scale_log2) : 1.0f;  // 0 on the first block
+            m_used = m_new;
+            const float mneg = -m_used * scale_log2;
+
+            // P = 2^((s - m_used) * c) in registers (bf16 pairs); row sum in fp32. Overlaps PV(j-1) on the tensor core.
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float p0 = ex2_approx4(fmaf(__uint_as_float(sv[2 * i]), scale_log2, mneg));
+                const float a1 = fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, mneg);
+                const float p1 = (i & 1) ? ex2_fma4(a1) : ex2_approx4(a1);
+                rs4[i & 3] += p0 + p1;
+                pk[i] = pack_bf16x2(p0, p1);
+            }
+            l_run = fmaf(l_run, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+
+            // PV(j-1) must have retired before O is rescaled and before the (single) P buffer is overwritten
+            if (j >= 1) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tcgen05_fence_after();
+                if (any_need) {
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         uint32_t v[32];
@@ -204,35 +231,14 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tmem_st_wait();
                     tcgen05_fence_before();
                 }
-                l_run *= alpha;
-                m_used = m_new;
             }
-            const float mneg = -m_used * scale_log2;
-
-            // P = 2^((s - m_used) * c) -> bf16 into the swizzled P buffer s; row sum in fp32
-            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-            uint8_t* prow = sP + s * k4PBytes + r * 128;
+            uint8_t* prow = sP + r * 128;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float p0 = ex2_approx4(fmaf(__uint_as_float(sv[c * 32 + 2 * i]), scale_log2, mneg));
-                    const float a1 = fmaf(__uint_as_float(sv[c * 32 + 2 * i + 1]), scale_log2, mneg);
-                    const float p1 = (i & 1) ? ex2_fma4(a1) : ex2_approx4(a1);
-                    rs4[i & 3] += p0 + p1;
-                    pk[i] = pack_bf16x2(p0, p1);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int lc = c * 4 + q;
-                    *reinterpret_cast<uint4*>(prow + ((lc ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                }
-            }
-            l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            for (int lc = 0; lc < 8; ++lc)
+                *reinterpret_cast<uint4*>(prow + ((lc ^ (r & 7)) << 4)) = make_uint4(pk[4 * lc], pk[4 * lc + 1], pk[4 * lc + 2], pk[4 * lc + 3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[s]);
+            if (lane == 0) mbar_arrive(p_full);
         }
         // epilogue: O / l
         mbar_wait(pv_done, (n_kv - 1) & 1);
@@ -287,6 +293,7 @@ int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfl
     static bool attr_set = false;
     if (!attr_set) {
         MMDP_CUDA(cudaFuncSetAttribute(attention_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k4Smem));
+        MMDP_CUDA(cudaFuncSetAttribute(attention_v4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     dim3 grid((L + 127) / 128, H, B);
