@@ -1,0 +1,285 @@
+// Attention forward v6 (default): softmax(Q K^T / sqrt(128)) V for head_dim 128, no mask, whole-sequence KV.
+// Same math / layouts / interface as attention.cu (v3); restructured around tensor memory after three ncu passes
+// (profiles/r01/README.md):
+//   * one CTA = one 128-row query tile of one head; KV blocks of 64; 7 warps: 4 softmax (thread = query row), K producer,
+//     MMA issuer, V^T producer; TWO CTAs per SM (112 KB smem, 256 TMEM columns, 107 registers each) so that one CTA's
+//     MMAs run under the other's softmax;
+//   * S = Q K^T (128 x 64 fp32) is double-buffered in TMEM columns 0..127, the output accumulator O (128 x 128 fp32)
+//     lives in columns 128..255 for the whole KV loop (tcgen05.mma accumulate) - no O registers in the softmax threads;
+//   * P never touches shared memory: the softmax threads write the bf16 pairs with tcgen05.st into the TMEM columns of the
+//     S buffer they were read from, and the PV MMA takes its A operand from tensor memory (tcgen05.mma [d], [a], b_desc).
+//     That removes the st.shared + fence.proxy.async of the smem route (15 % of the softmax warps' samples before);
+//   * lazy rescale (FlashAttention-4): the running max m_used is only raised when a row max exceeds it by more than 2^8;
+//     only then O and l are multiplied by 2^(m_old - m_new) through tcgen05.ld / tcgen05.st;
+//   * K (3 stages) and V^T (2 stages) tiles have their own producer warps: a single in-order producer held the next K tile
+//     back until the previous V^T slot was free, and the softmax warps waited 25 % of their time for S;
+//   * the S buffers need no "empty" barrier: PV(j) (which waits for P(j), i.e. for the softmax to be done with S(j)) is
+//     issued before QK(j+2) and the tensor core executes one thread's MMAs in order;
+//   * packed-fp32 softmax arithmetic (attention_math.cuh): 3 instructions per score.
+// Measured (B=1, L=2414, H=32): 697 TFLOP/s isolated, 573 TFLOP/s inside the power-capped denoising loop.
+#include "mmdp_internal.h"
+#include "ptx.cuh"
+#include "attention_math.cuh"
+
+namespace mmdp {
+
+static constexpr int k6Threads = 224;  // 4 softmax warps, K producer, MMA issuer, V producer
+static constexpr int k6BKV = 64;
+static constexpr int k6KStages = 3;
+static constexpr int k6VStages = 2;
+static constexpr int k6QBytes = 128 * 128 * 2;    // 32 KB (two 64-column halves)
+static constexpr int k6KBytes = k6BKV * 128 * 2;  // 16 KB (two halves of 64 rows x 64 cols)
+static constexpr int k6VBytes = 128 * k6BKV * 2;  // 16 KB (128 d rows x 64 kv)
+// smem: Q | K[3] | V[2] | barriers = 112.25 KB; no alignment slack (the dynamic smem window of a kernel without static
+// smem starts 1024-aligned; checked at run time) so that two CTAs fit into the 227 KB of an SM
+static constexpr int k6Smem = k6QBytes + k6KStages * k6KBytes + k6VStages * k6VBytes + 256;
+
+__global__ void __launch_bounds__(k6Threads, 2)
+attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
+                    float scale_log2) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+        printf("mmdp: attention smem base not 1024-byte aligned\n");
+        __trap();
+    }
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + k6QBytes;
+    uint8_t* sV = sK + k6KStages * k6KBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + k6VStages * k6VBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;    // [3]
+    uint64_t* k_empty = bars + 4;   // [3]
+    uint64_t* v_full = bars + 7;    // [2]
+    uint64_t* v_empty = bars + 9;   // [2]
+    uint64_t* s_full = bars + 11;   // [2]
+    uint64_t* p_full = bars + 13;   // [2]
+    uint64_t* pv_done = bars + 15;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int n_kv = (L + k6BKV - 1) / k6BKV;
+
+    if (warp == 5 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < k6KStages; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1);
+            mbar_init(&p_full[s], 4);
+        }
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmVt);
+        }
+        __syncwarp();
+        tmem_alloc<256>(tmem_ptr);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    // S[0] cols 0..63, S[1] cols 64..127 (P(j) = packed bf16 pairs in the first 32 columns of S[j & 1]), O cols 128..255
+    const uint32_t tS0 = tmem_base, tO = tmem_base + 128;
+
+    if (warp == 4) {
+        // ===================== TMA producer: Q, then the K tiles =====================
+        if (lane == 0) {
+            const int qrow0 = b * L + qt * 128;
+            mbar_expect_tx(q_full, k6QBytes);
+            tma_load_2d(sQ, &tmQ, q_full, h * 128, qrow0);
+            tma_load_2d(sQ + k6QBytes / 2, &tmQ, q_full, h * 128 + 64, qrow0);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                const int kv0 = j * k6BKV;
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], k6KBytes);
+                tma_load_2d(sK + st * k6KBytes, &tmK, &k_full[st], h * 128, b * L + kv0);
+                tma_load_2d(sK + st * k6KBytes + k6KBytes / 2, &tmK, &k_full[st], h * 128 + 64, b * L + kv0);
+                if (++st == k6KStages) { st = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 6) {
+        // ===================== TMA producer: V^T tiles =====================
+        if (lane == 0) {
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j & 1;
+                mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&v_full[st], k6VBytes);
+                tma_load_2d(sV + st * k6VBytes, &tmVt, &v_full[st], j * k6BKV, (b * H + h) * 128);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(128, k6BKV);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128);
+            const uint32_t aQ = smem_u32(sQ);
+            mbar_wait(q_full, 0);
+            int kst = 0;
+            uint32_t kph = 0;
+            for (int j = 0; j <= n_kv; ++j) {
+                if (j < n_kv) {
+                    // S[j & 1] = Q K(j)^T. The buffer is free: PV(j-2), which read P(j-2) from it, was issued in the
+                    // previous iteration (the tensor core executes this thread's MMAs in order) and waited for p_full.
+                    const uint32_t aK = smem_u32(sK + kst * k6KBytes);
+                    mbar_wait(&k_full[kst], kph);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {  // K dimension = head_dim 128: two 64-column halves of Q and K
+                        const uint32_t qoff = (k >> 2) * (k6QBytes / 2), koff = (k >> 2) * (k6KBytes / 2);
+                        umma_bf16_ss(tS0 + (j & 1) * k6BKV, umma_desc_kmajor_sw128(aQ + qoff) + (k & 3) * 2,
+                                     umma_desc_kmajor_sw128(aK + koff) + (k & 3) * 2, idesc_qk, k != 0);
+                    }
+                    umma_commit(&k_empty[kst]);
+                    umma_commit(&s_full[j & 1]);
+                    if (++kst == k6KStages) { kst = 0; kph ^= 1; }
+                }
+                if (j >= 1) {
+                    // O += P(j-1) V(j-1): A = P from tensor memory (8 columns per K=16 step)
+                    const int jj = j - 1, s = jj & 1;
+                    const uint32_t u = (jj >> 1) & 1;
+                    const uint32_t aV = smem_u32(sV + s * k6VBytes);
+                    mbar_wait(&v_full[s], u);
+                    mbar_wait(&p_full[s], u);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int k = 0; k < k6BKV / 16; ++k)
+                        umma_bf16_ts(tO, tS0 + s * k6BKV + k * 8, umma_desc_kmajor_sw128(aV) + k * 2, idesc_pv, (jj | k) != 0);
+                    umma_commit(&v_empty[s]);
+                    umma_commit(pv_done);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== softmax (warps 0..3, thread = query row) =====================
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        float m_used = -INFINITY, l_run = 0.f;
+        constexpr float kLazy = 8.0f;  // raise the running max only when it is exceeded by more than 2^8
+
+        for (int j = 0; j < n_kv; ++j) {
+            const int s = j & 1;
+            const int nvalid = L - j * k6BKV;
+            mbar_wait(&s_full[s], (j >> 1) & 1);
+            tcgen05_fence_after();
+            uint32_t sv[64];
+            tmem_ld_32x32b_x32(tS0 + s * k6BKV + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32b_x32(tS0 + s * k6BKV + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_wait();
+            if (nvalid < 64) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
+            }
+            float m8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m8[i] = __uint_as_float(sv[i]);
+#pragma unroll
+            for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(sv[i]));
+            const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+
+            // lazy rescale decision: only when this row's max exceeds the max in use by more than 2^kLazy (always on block 0)
+            const bool need = (mx - m_used) * scale_log2 > kLazy;  // m_used = -inf on block 0 -> true
+            const bool any_need = __any_sync(0xffffffffu, need);
+            const float m_new = need ? mx : m_used;
+            const float alpha = need ? ex2_mufu((m_used - m_new) * scale_log2) : 1.0f;  // 0 on the first block
+            m_used = m_new;
+            const float mneg = -m_used * scale_log2;
+
+            // P = 2^((s - m_used) * c) as bf16 pairs; row sum in fp32 (packed-fp32 arithmetic, see attention_math.cuh)
+            uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+            uint32_t pk[32];
+            softmax_exp_block<64>(sv, scale_log2, mneg, pk, acc);
+            l_run = fmaf(l_run, alpha, f32x2_sum4(acc));
+
+            if (any_need && j >= 1) {
+                // rare: rescale O (TMEM). PV(j-1) must have retired first; PV(j) cannot start before this P is published.
+                mbar_wait(pv_done, (j - 1) & 1);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                    tmem_st_32x32b_x32(tO + lane_off + c * 32, v);
+                }
+            }
+            // publish P(j) in the first 32 columns of S[s] (this row's 64 S values are in registers)
+            tmem_st_32x32b_x32(tS0 + s * k6BKV + lane_off, pk);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[s]);
+        }
+        // epilogue: O / l
+        mbar_wait(pv_done, (n_kv - 1) & 1);
+        tcgen05_fence_after();
+        const int qrow = qt * 128 + r;
+        const float inv_l = 1.0f / l_run;
+        __nv_bfloat16* orow = out + (size_t)(b * L + (qrow < L ? qrow : 0)) * d_model + h * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (qrow < L) {
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
+                uint4* d4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tcgen05_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
+                     int Lpad, float scale, cudaStream_t stream) {
+    if (B <= 0 || H <= 0 || L <= 0) return set_error("attention: empty problem");
+    if (Lpad < L || (Lpad % 8)) return set_error("attention: Lpad must be >= L and a multiple of 8");
+    const int d_model = H * 128;
+    CUtensorMap tmQ, tmK, tmVt;
+    if (make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, 128, 64)) return -1;
+    if (make_tmap_2d_bf16(&tmK, k, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, k6BKV, 64)) return -1;
+    if (make_tmap_2d_bf16(&tmVt, vt, (uint64_t)B * H * 128, (uint64_t)Lpad, (uint64_t)Lpad, 128, 64)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMDP_CUDA(cudaFuncSetAttribute(attention_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k6Smem));
+        MMDP_CUDA(cudaFuncSetAttribute(attention_v6_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    dim3 grid((L + 127) / 128, H, B);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)L * L * 128, stream);
+    attention_v6_kernel<<<grid, k6Threads, k6Smem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
+    MMDP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mmdp

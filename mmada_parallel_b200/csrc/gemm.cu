@@ -302,11 +302,11 @@ static int g_pair_mode = -1;
 int gemm_pair_mode() {
     if (g_pair_mode < 0) {
         const char* e = getenv("MMDP_GEMM_PAIR");
-        g_pair_mode = (e && e[0] == '1') ? 1 : 0;
+        g_pair_mode = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
     }
     return g_pair_mode;
 }
-void set_gemm_pair_mode(int on) { g_pair_mode = on ? 1 : 0; }
+void set_gemm_pair_mode(int on) { g_pair_mode = (on == 2) ? 2 : (on ? 1 : 0); }
 
 int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa,
@@ -339,7 +339,9 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
             return set_error("gemm: unknown epilogue");
     }
     // kernel selection: MMDP_GEMM_PAIR=1 routes large problems to the CTA-pair (cta_group::2) kernel of gemm2.cu
-    if (gemm_pair_mode() && M > 256) return gemm_bf16_pair(epi, A, lda, W, ldw, M, N, K, C, ldc, resid, ldr, qa, stream);
+    // mode 2 (auto): only where the pair kernel measured faster - many-row problems with wide N (M pads to 256-row tiles)
+    const int pm = gemm_pair_mode();
+    if ((pm == 1 && M > 256) || (pm == 2 && M >= 4096 && N >= 8192)) return gemm_bf16_pair(epi, A, lda, W, ldw, M, N, K, C, ldc, resid, ldr, qa, stream);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;

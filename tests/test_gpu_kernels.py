@@ -133,6 +133,37 @@ def test_qkv_rope_and_attention(B, L, H):
     assert not torch.isnan(o.float()).any()
 
 
+@pytest.mark.parametrize("version", [6, 5, 3])
+def test_attention_versions_and_lazy_rescale(version):
+    """Every attention kernel generation (csrc/attention_dispatch.cu) against the fp32 reference, on random scores and on
+    scores whose magnitude grows along the KV axis, so that the running row max jumps by far more than the lazy-rescale
+    threshold (2^8) in many KV blocks - the path that rescales the TMEM-resident O accumulator."""
+    from mmada_parallel_b200 import _lib
+    scale = 1.0 / math.sqrt(128.0)
+    _lib.lib.mmdp_set_attention_version(version)
+    try:
+        for B, L, H, grow in [(2, 333, 2, 0.0), (1, 1000, 2, 60.0), (1, 129, 1, 200.0)]:
+            torch.manual_seed(version * 100 + L)
+            d, M = H * 128, B * L
+            Lpad = (L + 7) // 8 * 8
+            q = bf(torch.randn(M, d, device="cuda"))
+            ramp = 1.0 + grow * (torch.arange(M, device="cuda") % L).float()[:, None] / L
+            k = bf(torch.randn(M, d, device="cuda") * ramp)
+            v = bf(torch.randn(M, d, device="cuda"))
+            vt = torch.zeros(B, H, 128, Lpad, dtype=torch.bfloat16, device="cuda")
+            vt[..., :L] = v.view(B, L, H, 128).permute(0, 2, 3, 1)
+            o = _lib.attention(q, k, vt, B, H, L, scale)
+            qh = q.view(B, L, H, 128).transpose(1, 2).float()
+            kh = k.view(B, L, H, 128).transpose(1, 2).float()
+            vh = v.view(B, L, H, 128).transpose(1, 2).float()
+            o_ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1) @ vh).transpose(1, 2).reshape(M, d)
+            err = (o.float() - o_ref).abs().max().item()
+            assert not torch.isnan(o.float()).any(), (version, L, grow)
+            assert err < 2e-2 * max(1.0, vh.abs().max().item()), (version, L, grow, err)
+    finally:
+        _lib.lib.mmdp_set_attention_version(6)
+
+
 def test_rmsnorm_embed_lfq():
     from mmada_parallel_b200 import _lib
     torch.manual_seed(3)

@@ -5,9 +5,10 @@ sys.path.insert(0, ROOT)
 import torch
 from mmada_parallel_b200 import _lib
 torch.manual_seed(0)
-a = (torch.randn(2414, 4096, device="cuda") * 0.5).to(torch.bfloat16)
+M = int(os.environ.get("MMDP_PROF_M", "7242"))
+a = (torch.randn(M, 4096, device="cuda") * 0.5).to(torch.bfloat16)
 w = (torch.randn(12288, 4096, device="cuda") * 0.05).to(torch.bfloat16)
-out = torch.empty(2414, 12288, dtype=torch.bfloat16, device="cuda")
+out = torch.empty(M, 12288, dtype=torch.bfloat16, device="cuda")
 for mode in (1, 0):
     _lib.lib.mmdp_set_gemm_pair(mode)
     for _ in range(3):
