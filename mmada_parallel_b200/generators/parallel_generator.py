@@ -110,61 +110,68 @@ class DenoiseState:
         return n
 
 
+def denoise_step(st: DenoiseState, step: int, is_img: bool, k_transfer: int, noise: "_Noise", text_steps: int,
+                 temperature: float, text_temperature: float, cfg_scale: float, cfg_img: float, noise_schedule,
+                 text_vocab_size: int, codebook_size: int, _trace: Optional[list] = None) -> None:
+    """One iteration of the step loop (parallel_generator.py:177-344; the preview loop app.py:177-305 runs the same body)
+    on device-resident state. No host<->device synchronisation happens in here."""
+    model, ids, V, n_text, seq_len = st.model, st.ids, st.model.vocab_rows, st.n_text, st.seq_len
+    # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
+    model.forward_rows(ids, rows_a=st.text_rows, out_a=st.text_logits, rows_b=st.pos if is_img else None,
+                       col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.cond_vq if is_img else None)
+    # ---- text step (:181-217). A fully un-masked span makes the kernel a no-op, like the `.sum() > 0` guard.
+    un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
+    check(lib.mmdp_text_step(ptr(st.text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
+                             ids.data_ptr() + st.text_start * 8, MASK_TOKEN, int(k_transfer), ptr(st.x0_ws), ptr(st.conf_ws),
+                             stream_ptr()))
+    if _trace is not None:
+        _trace.append({"step": step, "ids_after_text": ids[0].clone()})
+    if not is_img:
+        return
+    # ---- image step (:220-344)
+    ua = ub = None
+    if st.use_uncond:
+        if cfg_scale != 0.0:
+            st.scratch_ids.copy_(ids)
+            if st.unc_t_ids is not None:
+                st.scratch_ids[:, : st.unc_t_ids.shape[1]] = st.unc_t_ids
+            model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_t_vq)
+            ua = st.unc_t_vq
+        if cfg_img != 0.0:
+            st.scratch_ids.copy_(ids)
+            if st.unc_i_ids is not None:
+                st.scratch_ids[:, : st.unc_i_ids.shape[1]] = st.unc_i_ids
+            model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_i_vq)
+            ub = st.unc_i_vq
+    elif st.zeros_vq is not None:
+        # no uncond inputs: the reference mixes against zeros (:277-278)
+        ua = st.zeros_vq if cfg_scale != 0.0 else None
+        ub = st.zeros_vq if cfg_img != 0.0 else None
+    q = noise.exponential((seq_len, codebook_size)) if temperature != 0 else None   # torch.multinomial's draw (:299-302)
+    ratio = 1.0 * (step + 1) / text_steps
+    img_temp = temperature * (1.0 - ratio)                                           # :330
+    rn = noise.randn((1, seq_len))                                                   # mask_by_random_topk (:30-31)
+    check(lib.mmdp_image_step(0, ptr(st.cond_vq), ptr(ua), ptr(ub), codebook_size, seq_len, codebook_size,
+                              float(cfg_scale), float(cfg_img), ptr(q), ptr(rn), float(img_temp),
+                              scheduled_mask_len(seq_len, step, text_steps, noise_schedule), ptr(ids), ptr(st.pos),
+                              MASK_TOKEN, text_vocab_size, ptr(st.sampled_ws), ptr(st.selp_ws), ptr(st.unk_ws), None,
+                              None, None, stream_ptr()))
+    if _trace is not None:
+        _trace[-1].update(sampled=st.sampled_ws.clone(), ids_after_image=ids[0].clone())
+
+
 def denoise_loop(st: DenoiseState, text_steps: int, timesteps: int, temperature: float, text_temperature: float,
                  cfg_scale: float, cfg_img: float, noise_schedule, generator, text_vocab_size: int, codebook_size: int,
                  _trace: Optional[list] = None) -> torch.Tensor:
     """The hot loop (parallel_generator.py:174-344) on device-resident state; returns the id buffer (device).
     No host<->device synchronisation happens in here."""
-    model, ids, V, n_text, seq_len = st.model, st.ids, st.model.vocab_rows, st.n_text, st.seq_len
     num_transfer = _num_transfer_row(st.total_masks, text_steps)                              # :153-154
     img_steps = set(image_generation_step_indices(text_steps, timesteps))                     # :157-159
-    noise = _Noise(generator, model.device)
-    ids_text_ptr = ids.data_ptr() + st.text_start * 8
+    noise = _Noise(generator, st.model.device)
     for step in range(text_steps):
-        is_img = step in img_steps
-        # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
-        model.forward_rows(ids, rows_a=st.text_rows, out_a=st.text_logits, rows_b=st.pos if is_img else None,
-                           col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.cond_vq if is_img else None)
-        # ---- text step (:181-217). A fully un-masked span makes the kernel a no-op, like the `.sum() > 0` guard.
-        un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
-        check(lib.mmdp_text_step(ptr(st.text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
-                                 ids_text_ptr, MASK_TOKEN, int(num_transfer[step]), ptr(st.x0_ws), ptr(st.conf_ws),
-                                 stream_ptr()))
-        if _trace is not None:
-            _trace.append({"step": step, "ids_after_text": ids[0].clone()})
-        if not is_img:
-            continue
-        # ---- image step (:220-344)
-        ua = ub = None
-        if st.use_uncond:
-            if cfg_scale != 0.0:
-                st.scratch_ids.copy_(ids)
-                if st.unc_t_ids is not None:
-                    st.scratch_ids[:, : st.unc_t_ids.shape[1]] = st.unc_t_ids
-                model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_t_vq)
-                ua = st.unc_t_vq
-            if cfg_img != 0.0:
-                st.scratch_ids.copy_(ids)
-                if st.unc_i_ids is not None:
-                    st.scratch_ids[:, : st.unc_i_ids.shape[1]] = st.unc_i_ids
-                model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_i_vq)
-                ub = st.unc_i_vq
-        elif st.zeros_vq is not None:
-            # no uncond inputs: the reference mixes against zeros (:277-278)
-            ua = st.zeros_vq if cfg_scale != 0.0 else None
-            ub = st.zeros_vq if cfg_img != 0.0 else None
-        q = noise.exponential((seq_len, codebook_size)) if temperature != 0 else None   # torch.multinomial's draw (:299-302)
-        ratio = 1.0 * (step + 1) / text_steps
-        img_temp = temperature * (1.0 - ratio)                                           # :330
-        rn = noise.randn((1, seq_len))                                                   # mask_by_random_topk (:30-31)
-        check(lib.mmdp_image_step(0, ptr(st.cond_vq), ptr(ua), ptr(ub), codebook_size, seq_len, codebook_size,
-                                  float(cfg_scale), float(cfg_img), ptr(q), ptr(rn), float(img_temp),
-                                  scheduled_mask_len(seq_len, step, text_steps, noise_schedule), ptr(ids), ptr(st.pos),
-                                  MASK_TOKEN, text_vocab_size, ptr(st.sampled_ws), ptr(st.selp_ws), ptr(st.unk_ws), None,
-                                  None, None, stream_ptr()))
-        if _trace is not None:
-            _trace[-1].update(sampled=st.sampled_ws.clone(), ids_after_image=ids[0].clone())
-    return ids
+        denoise_step(st, step, step in img_steps, num_transfer[step], noise, text_steps, temperature, text_temperature,
+                     cfg_scale, cfg_img, noise_schedule, text_vocab_size, codebook_size, _trace)
+    return st.ids
 
 
 @torch.no_grad()

@@ -45,3 +45,8 @@ def scheduled_mask_len(num_vq_tokens: int, step: int, text_steps: int, noise_sch
     ratio = 1.0 * (step + 1) / text_steps
     mask_ratio = noise_schedule(torch.tensor(ratio))
     return int((num_vq_tokens * mask_ratio).floor().item())
+
+
+def stepwise_image_step_indices(text_steps: int) -> List[int]:
+    """Image steps of the preview loop (A/app.py:162-164): 30 % of the steps, spread over the whole schedule."""
+    return torch.linspace(0, text_steps - 1, int(text_steps * 0.3)).round().int().tolist()

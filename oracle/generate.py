@@ -2,6 +2,7 @@
 
   generate_ti2ti       restates MMaDA-Parallel-A/generators/parallel_generator.py:102-368
   interleave_generate  restates MMaDA-Parallel-M/models/modeling_mmada.py:118-248
+  generate_ti2ti_stepwise / decode_text_with_masks  restate MMaDA-Parallel-A/app.py:143-398 / :102-140 (Gradio preview loop)
 The per-step arithmetic lives in oracle/sampling.py; this file restates the orchestration (schedules, which forwards
 run, how ids are rewritten). The python `.item()` loops of the reference are replaced by tensor indexing with the
 same results. Random draws come from sampling.NoiseSource (same calls, same order as the reference).
@@ -13,6 +14,54 @@ from typing import Optional
 import torch
 
 from . import sampling as S
+
+
+def _ti2ti_step(model, ids, step, is_img, k_transfer, pos, noise, text_start, text_end, seq_len, text_steps, temperature,
+                text_temperature, cfg_scale, cfg_img, uncon_text, uncon_image, noise_schedule, text_vocab_size, codebook_size,
+                stable_sort):
+    """One iteration of the step loop (parallel_generator.py:177-344 == app.py:177-305): cond forward, text step, and on
+    image steps the uncond forwards + image step. Rewrites `ids` in place; returns the trace record."""
+    MASK = S.MASK_TOKEN_A
+    cond_logits = model(ids, infer=True, use_cache=False).logits               # :178
+    noise.dtype = cond_logits.dtype
+    text_ids = ids[0, text_start:text_end]
+    if int((text_ids == MASK).sum()) > 0:                                      # :183
+        tl = cond_logits[0, text_start:text_end, :]
+        un = noise.text_uniform((1,) + tuple(tl.shape))[0].to(tl.device) if text_temperature != 0 else None
+        new_ids, x0, conf = S.text_step(tl, text_ids, MASK, k_transfer, temperature=text_temperature, uniform_noise=un)
+        ids[0, text_start:text_end] = new_ids
+    rec = {"step": step, "ids_after_text": ids[0].clone()}
+    if is_img:                                                                 # :220
+        tok = ids[0, pos]
+        vq = torch.where(tok == MASK, torch.tensor(-1), torch.clamp(tok - text_vocab_size, 0, codebook_size - 1))
+        sl = slice(text_vocab_size, text_vocab_size + codebook_size)
+        cond_vq = cond_logits[0, pos][:, sl]
+        unc_t = unc_i = None
+        if (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None):  # :243
+            ids_t, ids_i = ids.clone(), ids.clone()
+            if uncon_text is not None:
+                ids_t[:, : uncon_text.shape[1]] = uncon_text
+            if uncon_image is not None:
+                ids_i[:, : uncon_image.shape[1]] = uncon_image
+            # the reference runs both forwards (:263-264); the uncond_text result is unused when cfg_scale == 0
+            if cfg_scale != 0.0:
+                unc_t = model(ids_t, infer=True, use_cache=False).logits[0, pos][:, sl]
+            unc_i = model(ids_i, infer=True, use_cache=False).logits[0, pos][:, sl]
+        else:
+            unc_t = torch.zeros_like(cond_vq)                                  # :277-278
+            unc_i = torch.zeros_like(cond_vq)
+        q = noise.multinomial_q(seq_len, codebook_size).to(cond_vq.device) if temperature != 0 else None
+        ratio = 1.0 * (step + 1) / text_steps
+        img_temp = temperature * (1.0 - ratio)                                 # :330
+        rn = noise.remask_randn((1, seq_len))[0].to(cond_vq.device)            # :333 -> :30-31 (always drawn)
+        out = S.image_step("A", cond_vq, unc_t, unc_i, cfg_scale, cfg_img, vq, MASK,
+                           S.sched_len(seq_len, step, text_steps, noise_schedule), img_temp, q, rn, codebook_size,
+                           stable=stable_sort)
+        fin = out["final"]
+        ids[0, pos] = torch.where(fin == -1, torch.tensor(MASK), fin + text_vocab_size)   # :339-344
+        rec.update(mask_len=out["mask_len"], sampled=out["sampled"].clone(), masking=out["masking"].clone(),
+                   ids_after_image=ids[0].clone())
+    return rec
 
 
 @torch.no_grad()
@@ -38,48 +87,10 @@ def generate_ti2ti(model, input_ids, text_start, text_end, image_start, seq_len,
     assert len(pos_map) == seq_len, f"Expected {seq_len} VQ tokens, got {len(pos_map)}"
     pos = torch.tensor(pos_map, dtype=torch.long)
     noise = S.NoiseSource(generator, dtype=torch.bfloat16)
-    dtype = None
     for step in range(text_steps):
-        cond_logits = model(ids, infer=True, use_cache=False).logits               # :178
-        dtype = cond_logits.dtype
-        noise.dtype = dtype
-        text_ids = ids[0, text_start:text_end]
-        if int((text_ids == MASK).sum()) > 0:                                      # :183
-            tl = cond_logits[0, text_start:text_end, :]
-            un = noise.text_uniform((1,) + tuple(tl.shape))[0].to(tl.device) if text_temperature != 0 else None
-            new_ids, x0, conf = S.text_step(tl, text_ids, MASK, num_transfer[step], temperature=text_temperature,
-                                            uniform_noise=un)
-            ids[0, text_start:text_end] = new_ids
-        rec = {"step": step, "ids_after_text": ids[0].clone()}
-        if step in img_steps:                                                      # :220
-            tok = ids[0, pos]
-            vq = torch.where(tok == MASK, torch.tensor(-1), torch.clamp(tok - text_vocab_size, 0, codebook_size - 1))
-            sl = slice(text_vocab_size, text_vocab_size + codebook_size)
-            cond_vq = cond_logits[0, pos][:, sl]
-            unc_t = unc_i = None
-            if (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None):  # :243
-                ids_t, ids_i = ids.clone(), ids.clone()
-                if uncon_text is not None:
-                    ids_t[:, : uncon_text.shape[1]] = uncon_text
-                if uncon_image is not None:
-                    ids_i[:, : uncon_image.shape[1]] = uncon_image
-                # the reference runs both forwards (:263-264); the uncond_text result is unused when cfg_scale == 0
-                if cfg_scale != 0.0:
-                    unc_t = model(ids_t, infer=True, use_cache=False).logits[0, pos][:, sl]
-                unc_i = model(ids_i, infer=True, use_cache=False).logits[0, pos][:, sl]
-            else:
-                unc_t = torch.zeros_like(cond_vq)                                  # :277-278
-                unc_i = torch.zeros_like(cond_vq)
-            q = noise.multinomial_q(seq_len, codebook_size).to(cond_vq.device) if temperature != 0 else None
-            ratio = 1.0 * (step + 1) / text_steps
-            img_temp = temperature * (1.0 - ratio)                                 # :330
-            rn = noise.remask_randn((1, seq_len))[0].to(cond_vq.device)            # :333 -> :30-31 (always drawn)
-            out = S.image_step("A", cond_vq, unc_t, unc_i, cfg_scale, cfg_img, vq, MASK,
-                               S.sched_len(seq_len, step, text_steps, noise_schedule), img_temp, q, rn, codebook_size,
-                               stable=stable_sort)
-            fin = out["final"]
-            ids[0, pos] = torch.where(fin == -1, torch.tensor(MASK), fin + text_vocab_size)   # :339-344
-            rec.update(mask_len=out["mask_len"], sampled=out["sampled"].clone(), ids_after_image=ids[0].clone())
+        rec = _ti2ti_step(model, ids, step, step in img_steps, num_transfer[step], pos, noise, text_start, text_end, seq_len,
+                          text_steps, temperature, text_temperature, cfg_scale, cfg_img, uncon_text, uncon_image,
+                          noise_schedule, text_vocab_size, codebook_size, stable_sort)
         if trace is not None:
             trace.append(rec)
     text_tokens = [t for t in ids[0, text_start:text_end].tolist() if t != MASK]    # :348-349
@@ -94,6 +105,96 @@ def generate_ti2ti(model, input_ids, text_start, text_end, image_start, seq_len,
         else:
             image_tokens.append(int(torch.randint(0, codebook_size, (1,)).item()))
     return image_tokens, generated_text
+
+
+class PieceTokenizer:
+    """Stand-in tokenizer for pinning / tests (no tokenizer files offline): one printable piece per id; some ids decode to
+    a blank, to nothing, or raise, to exercise every branch of decode_text_with_masks (app.py:122-131)."""
+
+    def decode(self, ids, skip_special_tokens=False, clean_up_tokenization_spaces=False):
+        t = int(ids[0])
+        if t % 11 == 0:
+            return " "
+        if t % 13 == 0:
+            return ""
+        if t % 17 == 0:
+            raise KeyError(t)
+        return f"<{t}>"
+
+
+def decode_text_with_masks(ids, text_start, text_end, tokenizer, mask_token) -> str:
+    """app.py:102-140: text span as a string, runs of masks rendered as blocks (long runs abbreviated)."""
+    def run(n):
+        return "\u2593" * n if n <= 10 else f"\u2593\u2593\u2593\u2593\u2593[...{n - 5} more]"
+    parts, masks = [], 0
+    for t in ids[0, text_start:text_end].cpu().tolist():
+        if t == mask_token:
+            masks += 1
+            continue
+        if masks > 0:
+            parts.append(run(masks))
+            masks = 0
+        try:
+            txt = tokenizer.decode([t], skip_special_tokens=False, clean_up_tokenization_spaces=False)
+            if txt.strip() or txt in [" ", "\n", "\t"]:
+                parts.append(txt)
+        except Exception:                                                          # app.py:131 (bare except)
+            parts.append(f"[{t}]")
+    if masks > 0:
+        parts.append(run(masks))
+    return "".join(parts)
+
+
+def stepwise_image_step_indices(text_steps: int) -> list:
+    """app.py:162-164: 30 % of the steps, spread over the whole schedule."""
+    return torch.linspace(0, text_steps - 1, int(text_steps * 0.3)).round().int().tolist()
+
+
+def generate_ti2ti_stepwise(model, input_ids, text_start, text_end, image_start, seq_len, newline_every, text_steps=100,
+                            temperature=1.0, text_temperature=0.7, cfg_scale=0.0, cfg_img=4.0, uncon_text=None,
+                            uncon_image=None, tokenizer=None, remasking="low_confidence", noise_schedule=S.cosine_schedule,
+                            generator=None, text_vocab_size=126356, codebook_size=8192, preview=None,
+                            stable_sort: bool = False, trace: Optional[list] = None):
+    """Generator restating app.py:143-398. Yields (step, text_display, image, status) at the reference's cadence.
+    `preview(sampled_ids[1, N] int64, masking[N] bool | None, masked_idx list | None)` stands for decode_vq_to_image +
+    the grey overlay of still-masked cells (app.py:307-335, :367-396); its return value is yielded as the image."""
+    if remasking != "low_confidence":
+        raise NotImplementedError(remasking)
+    MASK, NL = S.MASK_TOKEN_A, S.NEW_LINE_A
+    ids = input_ids.clone()
+    total_image_len = seq_len + seq_len // newline_every
+    n_masked = int((ids[0, text_start:text_end] == MASK).sum())
+    num_transfer = S.get_num_transfer_tokens_a(n_masked, text_steps)
+    img_steps = stepwise_image_step_indices(text_steps)
+    pos_map = [i for i in range(image_start, image_start + total_image_len) if int(ids[0, i]) != NL]
+    pos = torch.tensor(pos_map, dtype=torch.long)
+    noise = S.NoiseSource(generator, dtype=torch.bfloat16)
+    last_image = None
+    yield 0, decode_text_with_masks(ids, text_start, text_end, tokenizer, MASK), None, f"Step 0/{text_steps}"
+    for step in range(text_steps):
+        is_img = step in img_steps
+        rec = _ti2ti_step(model, ids, step, is_img, num_transfer[step], pos, noise, text_start, text_end, seq_len, text_steps,
+                          temperature, text_temperature, cfg_scale, cfg_img, uncon_text, uncon_image, noise_schedule,
+                          text_vocab_size, codebook_size, stable_sort)
+        if trace is not None:
+            trace.append(rec)
+        if is_img and preview is not None:
+            last_image = preview(rec["sampled"].unsqueeze(0), rec["masking"], None)   # decode of the PRE-remask sample
+        text_display = decode_text_with_masks(ids, text_start, text_end, tokenizer, MASK)
+        remaining = int((ids[0, text_start:text_end] == MASK).sum())
+        status = f"Step {step + 1}/{text_steps} | Text: {(1 - remaining / (text_end - text_start)) * 100:.1f}%"
+        if is_img:
+            img_left = int((ids[0, pos] == MASK).sum())
+            status += f" | Image: {(1 - img_left / seq_len) * 100:.1f}%"
+        if step % 5 == 0 or is_img or step == text_steps - 1:                        # app.py:345
+            yield step + 1, text_display, last_image, status
+    final_text = decode_text_with_masks(ids, text_start, text_end, tokenizer, MASK)
+    if last_image is None and preview is not None:                                   # app.py:352-396 (no image step ran)
+        tok = ids[0, pos]
+        masked = (tok == MASK).nonzero().flatten().tolist()
+        vq = torch.where(tok == MASK, torch.tensor(codebook_size // 2), torch.clamp(tok - text_vocab_size, 0, codebook_size - 1))
+        last_image = preview(vq.unsqueeze(0), None, masked)
+    yield text_steps, final_text, last_image, "\u2713 Complete"
 
 
 @torch.no_grad()

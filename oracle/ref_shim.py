@@ -87,3 +87,20 @@ def load_m():
     except Exception:  # pragma: no cover - magvit import is optional for the sampler fixtures
         mv = None
     return mm, sm, mv
+
+
+def load_app():
+    """MMaDA-Parallel-A/app.py (Gradio demo) with its UI / diffusers imports stubbed: the module builds its Blocks at import
+    time, so `gradio` is a MagicMock; `utils.image_utils` imports diffusers at module level."""
+    from unittest.mock import MagicMock
+    if REF_A not in sys.path:
+        sys.path.insert(0, REF_A)
+    sys.modules.setdefault("gradio", MagicMock())
+    if "diffusers" not in sys.modules:
+        d = types.ModuleType("diffusers")
+        d.VQModel = object
+        dp = types.ModuleType("diffusers.image_processor")
+        dp.VaeImageProcessor = object
+        sys.modules["diffusers"] = d
+        sys.modules["diffusers.image_processor"] = dp
+    return importlib.import_module("app")

@@ -195,3 +195,79 @@ def test_full_size_properties():
         assert d.max() <= 4 * want.float().abs().max() * 2.0 ** -8, float(d.max())
         assert (got != want).float().mean() < 0.25  # isolated 1-ulp flips propagated through one layer + the head
     assert torch.isfinite(a2.float()).all() and a2.float().abs().max() > 0.1
+
+
+class _RecordingDecoder:
+    """Native-protocol VQ decoder stand-in: records the ids it is asked to decode, returns a black image."""
+
+    def __init__(self, upscale=16):
+        from types import SimpleNamespace
+        self.decoder = SimpleNamespace(upscale=upscale)
+        self.calls = []
+
+    def decode_code(self, ids, shape=None):
+        self.calls.append(ids.clone().cpu())
+        h, w = shape
+        return -torch.ones(ids.shape[0], 3, h * self.decoder.upscale, w * self.decoder.upscale, device=ids.device)
+
+
+def test_generate_ti2ti_stepwise_lockstep_with_oracle():
+    """Preview loop (A/app.py:143-398): product generator == oracle generator on the B200's logits -
+    every yielded (step, text, status), the ids handed to the decoder, and the greyed-out (re-masked) cells."""
+    from mmada_parallel_b200.generators.stepwise import generate_ti2ti_stepwise
+    t = load_golden("trajectory_stepwise_tiny.pt")
+    model, cfg, _ = tiny_gpu_model(t["meta"])
+    lay, hw = t["layout"], t["image_hw"]
+    backed = GpuBackedOracleModel(model)
+    grid = int(lay["seq_len"] ** 0.5)
+    cell = hw // grid
+    for run in t["runs"]:
+        o_dec = []
+
+        def preview(sampled, masking, masked_idx):
+            o_dec.append(sampled.clone())
+            return masking.nonzero().flatten().tolist() if masking is not None else list(masked_idx)
+
+        ys_o = list(G.generate_ti2ti_stepwise(backed, lay["input_ids"], generator=torch.Generator().manual_seed(run["seed"]),
+                                              tokenizer=G.PieceTokenizer(), preview=preview, stable_sort=True, **_args(lay),
+                                              **run["kwargs"]))
+        dec = _RecordingDecoder()
+        before = lay["input_ids"].clone()
+        ys_g = list(generate_ti2ti_stepwise(model, lay["input_ids"], generator=torch.Generator().manual_seed(run["seed"]),
+                                            tokenizer=G.PieceTokenizer(), vqvae=dec, image_height=hw, image_width=hw,
+                                            **_args(lay), **run["kwargs"]))
+        assert torch.equal(before, lay["input_ids"])
+        assert [(s, txt, st) for s, txt, _, st in ys_g] == [(s, txt, st) for s, txt, _, st in ys_o], run["name"]
+        assert len(dec.calls) == len(o_dec) and all(torch.equal(a, b) for a, b in zip(dec.calls, o_dec)), run["name"]
+        for (_, _, img, _), (_, _, cells, _) in zip(ys_g, ys_o):
+            assert (img is None) == (cells is None)
+            if img is not None:
+                assert img.size == (hw, hw)
+                px = img.load()
+                grey = [i for i in range(grid * grid) if px[(i % grid) * cell + 1, (i // grid) * cell + 1] != (0, 0, 0)]
+                assert grey == cells, (run["name"], grey, cells)
+    with pytest.raises(NotImplementedError):
+        next(generate_ti2ti_stepwise(model, lay["input_ids"], remasking="random", **_args(lay)))
+    with pytest.raises(ValueError):  # no decoder: the reference would fail loading the aMUSEd VQ-VAE from vae_ckpt=None
+        list(generate_ti2ti_stepwise(model, lay["input_ids"], text_steps=2, tokenizer=G.PieceTokenizer(), **_args(lay)))
+
+
+def test_decode_vq_to_image_native_decoder():
+    """decode_vq_to_image (A/utils/image_utils.py:13-75) over the native MagViT decoder: PIL image of the requested size,
+    equal to the (x+1)/2 -> uint8 conversion of decode_code; ValueError on a length mismatch (:48-52)."""
+    from mmada_parallel_b200.magvit import MAGVITv2
+    from mmada_parallel_b200.utils.image_utils import decode_vq_to_image
+    from oracle import magvit as OM
+    cfg = OM.decoder_config(ch=32, ch_mult=(1, 1, 2, 2, 2), num_res_blocks=(1, 1, 1, 1, 1))
+    m = MAGVITv2(max_batch=1, ch=cfg.ch, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks, latent_hw=(4, 4))
+    m.load_state_dict(OM.make_weights(cfg, 5))
+    ids = torch.randint(0, 8192, (1, 16), generator=torch.Generator().manual_seed(1))
+    img = decode_vq_to_image(ids.cuda(), None, None, 64, 64, m)
+    assert img.size == (64, 64) and img.mode == "RGB"
+    want = ((m.decode_code(ids)[0] + 1) * 0.5).clamp(0, 1).permute(1, 2, 0).mul(255).round().to(torch.uint8).cpu()
+    import numpy as np
+    assert np.array_equal(np.asarray(img), want.numpy())
+    with pytest.raises(ValueError):
+        decode_vq_to_image(ids[:, :15].cuda(), None, None, 64, 64, m)
+    with pytest.raises(TypeError):
+        decode_vq_to_image(ids.cuda(), None, None, 64, 64, object())

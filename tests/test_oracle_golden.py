@@ -141,3 +141,29 @@ def test_magvit_encoder_matches_reference_golden():
     ids = g["ids"]
     side = int(ids.shape[1] ** 0.5)
     assert torch.equal(OM.lfq_indices(lfq_codebook_entry(ids, 13).view(ids.shape[0], 13, side, side), 13), ids)
+
+
+def test_stepwise_preview_loop_matches_reference_golden(tiny):
+    """oracle.generate.generate_ti2ti_stepwise == the reference's Gradio preview loop (A/app.py:143-398): every yielded
+    (step, text, status), the ids handed to the VQ decoder and the greyed-out cells (fixture made by
+    oracle/make_golden_stepwise.py from the real reference)."""
+    t = load_golden("trajectory_stepwise_tiny.pt")
+    model = tiny[3]
+    same_sort = sort_order_matches_fixture(load_golden("sampler_kat.pt"))  # tie order of torch.sort on this machine
+    lay = t["layout"]
+    args = {k: lay[k] for k in ("text_start", "text_end", "image_start", "seq_len", "newline_every", "uncon_text", "uncon_image")}
+    for run in t["runs"]:
+        decoded = []
+
+        def preview(sampled, masking, masked_idx):
+            decoded.append(sampled.clone())
+            return masking.nonzero().flatten().tolist() if masking is not None else list(masked_idx)
+
+        ys = list(G.generate_ti2ti_stepwise(model, lay["input_ids"], generator=torch.Generator().manual_seed(run["seed"]),
+                                            tokenizer=G.PieceTokenizer(), preview=preview, **args, **run["kwargs"]))
+        assert [s for s, _, _, _ in ys] == [y[0] for y in run["yields"]], run["name"]
+        assert len(decoded) == len(run["decoded"])
+        if same_sort:
+            assert [(s, txt, st, im is not None) for s, txt, im, st in ys] == [tuple(y) for y in run["yields"]], run["name"]
+            assert [im for _, _, im, _ in ys] == run["overlays"], run["name"]
+            assert all(torch.equal(a, b) for a, b in zip(decoded, run["decoded"]))
