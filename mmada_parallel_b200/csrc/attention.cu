@@ -107,7 +107,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     if (warp == 8) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const int qrow0 = b * L + qt * 128;
             mbar_expect_tx(q_full, kTile);
             tma_load_2d(sQ, &tmQ, q_full, h * 128, qrow0);
@@ -129,7 +129,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
             const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
             mbar_wait(q_full, 0);

@@ -109,7 +109,7 @@ attention_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     if (warp == 4) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const int qrow0 = b * L + qt * 128;
             mbar_expect_tx(q_full, k5TileBytes);
             tma_load_2d(sQ, &tmQ, q_full, h * 128, qrow0);
@@ -130,7 +130,7 @@ attention_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
             const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
             mbar_wait(q_full, 0);

@@ -95,7 +95,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     if (warp == 4) {
         // ===================== TMA producer: Q, then the K tiles =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const int qrow0 = b * L + qt * 128;
             mbar_expect_tx(q_full, k6QBytes);
             tma_load_2d(sQ, &tmQ, q_full, h * 128, qrow0);
@@ -114,7 +114,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
     } else if (warp == 6) {
         // ===================== TMA producer: V^T tiles =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             for (int j = 0; j < n_kv; ++j) {
                 const int st = j & 1;
                 mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
@@ -125,7 +125,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_qk = umma_idesc_bf16(128, k6BKV);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128);
             const uint32_t aQ = smem_u32(sQ);

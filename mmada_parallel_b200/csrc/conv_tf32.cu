@@ -84,7 +84,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_tiles = num_m * num_n;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_blk = tile % num_n, m_blk = tile / num_n;  // n fastest: CTAs running together share the A rows
@@ -101,7 +101,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_tf32(CBM, CBN);
             int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {

@@ -125,7 +125,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int s = 0;
             uint32_t ph = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -150,7 +150,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
+        if (leader && elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(2 * P_BM, BN);
             int s = 0;
             uint32_t ph = 0;

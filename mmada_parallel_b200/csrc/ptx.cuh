@@ -15,6 +15,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp (elect.sync). Code predicated on this is compiled as single-thread code: uniform-datapath
+// instructions (tcgen05.mma, tcgen05.commit, TMA) are issued directly instead of inside the per-active-thread loop ptxas
+// emits under an ordinary `lane == 0` branch.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // A hang on a fresh GPU box costs a strike; every barrier wait is bounded and traps instead.
 #ifndef MMDP_WAIT_SPIN_LIMIT
 #define MMDP_WAIT_SPIN_LIMIT (1u << 26)
