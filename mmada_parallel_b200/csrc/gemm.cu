@@ -90,7 +90,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int tile = blockIdx.x; tile < full_tiles + (has_unit ? 1 : 0) * gridDim.x; tile += gridDim.x) {
                 const bool is_unit = tile >= full_tiles;
                 const int tl = is_unit ? unit_tile : tile;
-                const int m_blk = tl % num_m, n_blk = tl / num_m;
+                int m_blk, n_blk;
+                gemm_tile_coords(tl, num_m, num_n, p.group_m, m_blk, n_blk);
                 const int kb_beg = is_unit ? unit_kb0 : 0, kb_end = is_unit ? unit_kb1 : num_k;
                 for (int kb = kb_beg; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -146,7 +147,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int tile = blockIdx.x; tile < full_tiles + (has_unit ? 1 : 0) * gridDim.x; tile += gridDim.x) {
             const bool is_unit = tile >= full_tiles;
             const int tl = is_unit ? unit_tile : tile;
-            const int m_blk = tl % num_m, n_blk = tl / num_m;
+            int m_blk, n_blk;
+            gemm_tile_coords(tl, num_m, num_n, p.group_m, m_blk, n_blk);
             mbar_wait(&tmem_full[as], aph);
             tcgen05_fence_after();
             const int row = m_blk * BM + ew * 32 + lane;
@@ -347,6 +349,25 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
     const GemmPlan pl = plan_gemm(epi, M, N, K);
     const int bn = pl.bn, grid = pl.grid;
+    // tile order (gemm_tile_coords): with many m-tiles, walk them in balanced groups of <= 40 so that one wave of 148 tiles
+    // spans ~30 m-tiles x ~5 n-tiles instead of all m-tiles x 2.6 n-tiles. Measured on M = 7242 (57 m-tiles, the B=3 batch
+    // of a caller that batches its CFG branches): +4..7 % on every body GEMM shape, DRAM reads 668 -> 362 MB; no gain below
+    // ~45 m-tiles, so M = 2414 keeps the plain order (profiles/r01/README.md). MMDP_GEMM_GROUP_M overrides: 0 = off, n > 0 =
+    // fixed group size.
+    static int group_m_env = -2;
+    if (group_m_env == -2) {
+        const char* e = getenv("MMDP_GEMM_GROUP_M");
+        group_m_env = e ? atoi(e) : -1;
+    }
+    {
+        const int num_m = (M + BM - 1) / BM;
+        int g = 0;
+        if (num_m > 45) {
+            const int ngroups = (num_m + 39) / 40;
+            g = (num_m + ngroups - 1) / ngroups;
+        }
+        p.group_m = group_m_env >= 0 ? group_m_env : g;
+    }
     if (pl.tail > 0) {
         if (ensure_splitk_workspace()) return -1;
         p.sk_tail = pl.tail; p.sk_splits = pl.splits; p.sk_kb_per = pl.kb_per; p.sk_ws = g_sk_ws; p.sk_cnt = g_sk_cnt;

@@ -24,7 +24,24 @@ struct GemmParams {
     int sk_tail, sk_splits, sk_kb_per;
     float* sk_ws;
     int* sk_cnt;
+    // tile order: group_m == 0 -> M-fastest over all m-tiles; > 0 -> M-fastest inside groups of group_m m-tiles, all n-tiles
+    // of a group before the next group (keeps the group's A rows L2-resident while the weights stream)
+    int group_m;
 };
+
+__device__ __forceinline__ void gemm_tile_coords(int tl, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+    if (group_m <= 0 || group_m >= num_m) {
+        m_blk = tl % num_m;
+        n_blk = tl / num_m;
+    } else {
+        const int per_group = group_m * num_n;
+        const int gid = tl / per_group, r = tl - gid * per_group;
+        const int first = gid * group_m;
+        const int gsz = (num_m - first < group_m) ? num_m - first : group_m;
+        m_blk = first + r % gsz;
+        n_blk = r / gsz;
+    }
+}
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t (&p)[16], int ncols_valid) {
     // dst is 16-B aligned when ldc % 8 == 0 and column offsets are multiples of 8

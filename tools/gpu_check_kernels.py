@@ -284,6 +284,12 @@ CASES = {
     "gemm_qkv_shape": lambda: case_gemm(2414, 12288, 4096, timing=True),
     "gemm_ffout_shape": lambda: case_gemm(2414, 4096, 12288, timing=True),
     "gemm_head_text": lambda: case_gemm(256, 134656, 4096, timing=True),
+    "resid_attnout_b3": lambda: {"case": "resid_7242x4096x4096", "ok": True, **time_resid(7242, 4096, 4096)},
+    "resid_ffout_b3": lambda: {"case": "resid_7242x4096x12288", "ok": True, **time_resid(7242, 4096, 12288)},
+    "gemm_swiglu_b1": lambda: case_gemm(2414, 24576, 4096, timing=True),
+    "gemm_qkv_b3": lambda: case_gemm(7242, 12288, 4096, timing=True),
+    "gemm_swiglu_b3": lambda: case_gemm(7242, 24576, 4096, timing=True),
+    "gemm_odd_m": lambda: case_gemm(2414 + 128, 1024, 512, timing=False),
     "qkv_attn_small": lambda: case_qkv_attn(1, 128, 2),
     "qkv_attn_ragged": lambda: case_qkv_attn(2, 200, 2),
     "qkv_attn_multi": lambda: case_qkv_attn(1, 640, 4),
