@@ -21,6 +21,8 @@
 #include "ptx.cuh"
 #include "attention_math.cuh"
 
+#include <stdlib.h>
+
 namespace mmdp {
 
 static constexpr int k6Threads = 224;  // 4 softmax warps, K producer, MMA issuer, V producer
@@ -34,6 +36,7 @@ static constexpr int k6VBytes = 128 * k6BKV * 2;  // 16 KB (128 d rows x 64 kv)
 // smem starts 1024-aligned; checked at run time) so that two CTAs fit into the 227 KB of an SM
 static constexpr int k6Smem = k6QBytes + k6KStages * k6KBytes + k6VStages * k6VBytes + 256;
 
+template <int POLY>
 __global__ void __launch_bounds__(k6Threads, 2)
 attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
@@ -205,7 +208,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // P = 2^((s - m_used) * c) as bf16 pairs; row sum in fp32 (packed-fp32 arithmetic, see attention_math.cuh)
             uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
             uint32_t pk[32];
-            softmax_exp_block<64>(sv, scale_log2, mneg, pk, acc);
+            softmax_exp_block<64, POLY>(sv, scale_log2, mneg, pk, acc);
             l_run = fmaf(l_run, alpha, f32x2_sum4(acc));
 
             if (any_need && j >= 1) {
@@ -268,16 +271,26 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     if (make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, 128, 64)) return -1;
     if (make_tmap_2d_bf16(&tmK, k, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, k6BKV, 64)) return -1;
     if (make_tmap_2d_bf16(&tmVt, vt, (uint64_t)B * H * 128, (uint64_t)Lpad, (uint64_t)Lpad, 128, 64)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMDP_CUDA(cudaFuncSetAttribute(attention_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k6Smem));
-        MMDP_CUDA(cudaFuncSetAttribute(attention_v6_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+    // share of exp2 evaluated on the FMA pipe: every POLY-th pair's second element (0 = none; default 4 = 1/8 of all exp2). MMDP_ATTN_POLY = 0|2|4|8.
+    static int poly = -1;
+    if (poly < 0) {
+        const char* e = getenv("MMDP_ATTN_POLY");
+        poly = e ? atoi(e) : 4;  // measured 914 / 916 / 925 / 889 TFLOP/s for 0 / 8 / 4 / 2 (B=1, L=2414, H=32)
+        if (poly != 0 && poly != 2 && poly != 8) poly = 4;
     }
     dim3 grid((L + 127) / 128, H, B);
     const float scale_log2 = scale * 1.4426950408889634f;
     LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)L * L * 128, stream);
-    attention_v6_kernel<<<grid, k6Threads, k6Smem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
+    auto launch = [&](auto kernel) -> int {
+        MMDP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k6Smem));
+        MMDP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        kernel<<<grid, k6Threads, k6Smem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
+        return 0;
+    };
+    if (poly == 2) { if (launch(attention_v6_kernel<2>)) return -1; }
+    else if (poly == 4) { if (launch(attention_v6_kernel<4>)) return -1; }
+    else if (poly == 8) { if (launch(attention_v6_kernel<8>)) return -1; }
+    else { if (launch(attention_v6_kernel<0>)) return -1; }
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }

@@ -7,14 +7,12 @@
 //   row sum      add.rn.f32x2   1 per pair (FADD2)
 //   bf16 pack    cvt.rn.bf16x2  1 per pair
 //   row max      3-input max    1 per pair (FMNMX3, formed by ptxas)
-// = 3 instructions per score. kPolyEvery > 0 moves every kPolyEvery-th exp2 of a pair's second element to the FMA pipe
-// (Cody-Waite split + cubic, ~9 instructions) for the day the MUFU pipe becomes the limiter again.
+// = 3 instructions per score. POLY > 0 moves the second exp2 of every POLY-th pair to the FMA pipe (Cody-Waite split +
+// cubic, ~9 instructions) to relieve the MUFU pipe (16 ex2 / clk / SM) once the kernel runs fast enough to load it.
 #pragma once
 #include <cstdint>
 
 namespace mmdp {
-
-static constexpr int kPolyEvery = 0;
 
 __device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
     uint64_t r;
@@ -51,7 +49,7 @@ __device__ __forceinline__ float ex2_poly(float x) {  // see attention.cu::ex2_f
 
 // P = 2^(s * c + mneg) for N (even) scores held as raw fp32 bits in sv; writes N/2 packed bf16 pairs to pk and adds the
 // fp32 row sum into four packed accumulators (8 independent chains).
-template <int N>
+template <int N, int POLY = 0>
 __device__ __forceinline__ void softmax_exp_block(const uint32_t* sv, float scale_log2, float mneg, uint32_t* pk, uint64_t (&acc)[4]) {
     const uint64_t c2 = f32x2_pack(scale_log2, scale_log2), m2 = f32x2_pack(mneg, mneg);
 #pragma unroll
@@ -59,7 +57,7 @@ __device__ __forceinline__ void softmax_exp_block(const uint32_t* sv, float scal
         float x0, x1;
         f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, m2), x0, x1);
         const float p0 = ex2_mufu(x0);
-        const float p1 = (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0) ? ex2_poly(x1) : ex2_mufu(x1);
+        const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_mufu(x1);
         acc[i & 3] = f32x2_add(acc[i & 3], f32x2_pack(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
     }
