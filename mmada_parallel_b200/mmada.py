@@ -1,5 +1,6 @@
 """Drop-in for the variant-M model object: `MMadaModelLM.interleave_generate`
-(MMaDA-Parallel-M/models/modeling_mmada.py:118-248) on top of the same native forward.
+(MMaDA-Parallel-M/models/modeling_mmada.py:118-248) and `MMadaModelLM.mmu_generate` (:619-691, SURVEY 8f rank 3, the
+generation mode M's validation loop calls) on top of the same native forward.
 
 Differences from variant A that are preserved here:
   * one forward per step over the CFG batch [cond; uncond] (B = 2), never B = 1 (:168-177);
@@ -123,3 +124,64 @@ class MMadaModelLM(LLaDAForMultiModalGeneration):
         return_image_ids = sampled_ws.to(torch.int64).unsqueeze(0)
         return_text_ids = both[0:1, -max_seq:].clone()
         return return_image_ids, return_text_ids
+
+    @torch.no_grad()
+    def mmu_generate(self, idx=None, input_embeddings=None, max_new_tokens=128, steps=128, block_length=128, temperature=0.0,
+                     top_k=None, eot_token=None, cfg_scale=0.0, remasking="low_confidence", mask_id=126336,
+                     attention_mask=None):
+        """Block-wise (semi-autoregressive) un-masking of `max_new_tokens` masks appended to the prompt `idx [B, P]`
+        (modeling_mmada.py:619-691); returns x [B, P + max_new_tokens] on the model device. Per step one forward over
+        [x] (or the CFG batch [x; x with its prompt masked]) restricted to the current block's rows, then the text-step
+        kernel per batch row: logits = un + (cfg + 1) * (l - un) in bf16 (:660), argmax, fp64 softmax confidence, the k
+        most confident masked positions committed (:676-683). Positions after the block carry confidence -inf in the
+        reference (:673) and earlier blocks are complete, so only the block's rows are evaluated.
+        Not built (raise): padding masks (`attention_mask` with zeros -> attention_bias), `temperature > 0` (fp64 Gumbel from
+        the global RNG, :49-60), `remasking='random'` (global RNG), `input_embeddings`."""
+        if idx is None or input_embeddings is not None:
+            raise NotImplementedError("mmu_generate: only token-id prompts (idx) are supported")
+        if attention_mask is not None and bool((attention_mask == 0).any()):
+            raise NotImplementedError("mmu_generate: padding masks (attention_bias) are not supported by the native attention")
+        if temperature != 0:
+            raise NotImplementedError("mmu_generate: temperature > 0 draws fp64 Gumbel noise from the global RNG in the reference")
+        if remasking != "low_confidence":
+            raise NotImplementedError(remasking)
+        dev = self.device
+        idx = idx.to(device=dev, dtype=torch.int64)
+        B, P = idx.shape
+        if bool((idx == mask_id).any()):
+            raise ValueError("mmu_generate: the prompt must not contain mask tokens")
+        assert max_new_tokens % block_length == 0                                              # :642
+        num_blocks = max_new_tokens // block_length
+        assert steps % num_blocks == 0                                                         # :645
+        steps = steps // num_blocks
+        L = P + max_new_tokens
+        use_cfg = cfg_scale > 0.0
+        nb = 2 * B if use_cfg else B
+        both = torch.full((nb, L), int(mask_id), dtype=torch.int64, device=dev)              # rows [x; un_x]
+        both[:B, :P] = idx                                                                     # un_x: prompt stays masked (:656)
+        V = self.vocab_rows
+        text_logits = torch.empty((nb * block_length, V), dtype=torch.bfloat16, device=dev)
+        x0_ws = torch.empty(block_length, dtype=torch.int64, device=dev)
+        conf_ws = torch.empty(block_length, dtype=torch.float64, device=dev)
+        num_transfer = get_num_transfer_tokens_m(block_length, steps)                          # every block starts all-masked
+        for blk in range(num_blocks):
+            bs = P + blk * block_length
+            rows = torch.cat([torch.arange(r * L + bs, r * L + bs + block_length, dtype=torch.int32, device=dev)
+                              for r in range(nb)])
+            for i in range(steps):
+                self.forward_rows(both, rows_a=rows, out_a=text_logits)
+                for j in range(B):
+                    cond = text_logits.data_ptr() + j * block_length * V * 2
+                    if use_cfg:
+                        unc = text_logits.data_ptr() + (B + j) * block_length * V * 2
+                        # kernel: c + cfg * (u - c) with c = un-logits, u = cond logits, cfg = cfg_scale + 1
+                        check(lib.mmdp_text_step(unc, cond, V, block_length, V, float(cfg_scale + 1), None, 0, 0.0,
+                                                 both.data_ptr() + (j * L + bs) * 8, int(mask_id), int(num_transfer[i]),
+                                                 ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+                    else:
+                        check(lib.mmdp_text_step(cond, None, V, block_length, V, 0.0, None, 0, 0.0,
+                                                 both.data_ptr() + (j * L + bs) * 8, int(mask_id), int(num_transfer[i]),
+                                                 ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+                if use_cfg:
+                    both[B:, P:] = both[:B, P:]
+        return both[:B].clone()

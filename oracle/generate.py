@@ -3,6 +3,7 @@
   generate_ti2ti       restates MMaDA-Parallel-A/generators/parallel_generator.py:102-368
   interleave_generate  restates MMaDA-Parallel-M/models/modeling_mmada.py:118-248
   generate_ti2ti_stepwise / decode_text_with_masks  restate MMaDA-Parallel-A/app.py:143-398 / :102-140 (Gradio preview loop)
+  mmu_generate         restates MMaDA-Parallel-M/models/modeling_mmada.py:619-691 (semi-autoregressive text generation)
 The per-step arithmetic lives in oracle/sampling.py; this file restates the orchestration (schedules, which forwards
 run, how ids are rewritten). The python `.item()` loops of the reference are replaced by tensor indexing with the
 same results. Random draws come from sampling.NoiseSource (same calls, same order as the reference).
@@ -247,3 +248,48 @@ def interleave_generate(model, input_ids, uncond_input_ids, text_cfg, image_cfg,
         if trace is not None:
             trace.append(rec)
     return sampled_ids, ids[:, -max_seq_length:]
+
+
+@torch.no_grad()
+def mmu_generate(model, idx, max_new_tokens=128, steps=128, block_length=128, temperature=0.0, cfg_scale=0.0,
+                 remasking="low_confidence", mask_id=126336, attention_mask=None, trace: Optional[list] = None):
+    """Restates MMadaModelLM.mmu_generate (modeling_mmada.py:619-691): LLaDA block-wise un-masking of `max_new_tokens`
+    masks appended to the prompt `idx [B, P]`. `model(ids[B', L]).logits`. Per step: forward (CFG: batch [x; x with the
+    prompt masked], logits = un + (cfg + 1) * (l - un)), argmax, fp64 softmax confidence, positions after the current block
+    excluded, the k most confident masked positions of each row committed. Returns x [B, P + max_new_tokens]."""
+    if attention_mask is not None and bool((attention_mask == 0).any()):
+        raise NotImplementedError("padding masks (attention_bias) are outside this restatement")
+    if temperature != 0:
+        raise NotImplementedError("add_gumbel_noise draws fp64 noise from the global RNG (modeling_mmada.py:49-60)")
+    if remasking != "low_confidence":
+        raise NotImplementedError(remasking)                                         # 'random' uses the global RNG
+    B, P = idx.shape
+    x = torch.full((B, P + max_new_tokens), mask_id, dtype=torch.long)
+    x[:, :P] = idx
+    prompt_index = x != mask_id
+    assert max_new_tokens % block_length == 0
+    num_blocks = max_new_tokens // block_length
+    assert steps % num_blocks == 0
+    steps = steps // num_blocks
+    for blk in range(num_blocks):
+        bs, be = P + blk * block_length, P + (blk + 1) * block_length
+        counts = (x[:, bs:be] == mask_id).sum(dim=1).tolist()
+        num_transfer = [S.get_num_transfer_tokens_m(int(c), steps) for c in counts]
+        for i in range(steps):
+            if cfg_scale > 0.0:
+                un_x = x.clone()
+                un_x[prompt_index] = mask_id
+                logits, un_logits = torch.chunk(model(torch.cat([x, un_x], dim=0)).logits, 2, dim=0)
+            else:
+                logits, un_logits = model(x).logits, None
+            for j in range(B):
+                # positions [be, L) carry confidence -inf (:673): only [0, be) can be selected
+                if un_logits is not None:   # un + (cfg + 1) * (l - un)  (:660)
+                    new_ids, x0, conf = S.text_step(un_logits[j, :be], x[j, :be], mask_id, num_transfer[j][i],
+                                                    uncond_logits=logits[j, :be], text_cfg=cfg_scale + 1)
+                else:
+                    new_ids, x0, conf = S.text_step(logits[j, :be], x[j, :be], mask_id, num_transfer[j][i])
+                x[j, :be] = new_ids
+            if trace is not None:
+                trace.append(x.clone())
+    return x

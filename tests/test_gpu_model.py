@@ -271,3 +271,32 @@ def test_decode_vq_to_image_native_decoder():
         decode_vq_to_image(ids[:, :15].cuda(), None, None, 64, 64, m)
     with pytest.raises(TypeError):
         decode_vq_to_image(ids.cuda(), None, None, 64, 64, object())
+
+
+def test_mmu_generate_lockstep_with_oracle():
+    """MMadaModelLM.mmu_generate (M/models/modeling_mmada.py:619-691): product == oracle on the B200's
+    logits, every id of every batch row; plus the golden outputs of the real reference as a reported agreement."""
+    from mmada_parallel_b200.mmada import MMadaModelLM
+    t = load_golden("trajectory_mmu_tiny.pt")
+    model, cfg, _ = tiny_gpu_model(t["meta"], cls=MMadaModelLM, max_batch=4)
+    backed = GpuBackedOracleModel(model)
+    for run in t["runs"]:
+        am = torch.ones_like(run["out"]) if run["ones_mask"] else None
+        want = G.mmu_generate(backed, run["idx"], attention_mask=am, **run["kwargs"])
+        before = run["idx"].clone()
+        got = model.mmu_generate(idx=run["idx"], attention_mask=am, **run["kwargs"])
+        assert torch.equal(before, run["idx"])
+        assert got.device.type == "cuda" and got.dtype == torch.int64 and tuple(got.shape) == tuple(run["out"].shape)
+        assert torch.equal(got.cpu(), want), run["name"]
+        assert int((got == 126336).sum()) == 0
+        new = got.cpu()[:, run["idx"].shape[1]:]
+        print(f"[golden mmu] {run['name']}: agreement with the CPU reference {float((new == run['out'][:, run['idx'].shape[1]:]).float().mean()):.3f}")
+    idx = t["runs"][0]["idx"]
+    with pytest.raises(NotImplementedError):
+        model.mmu_generate(idx=idx, temperature=0.3)
+    with pytest.raises(NotImplementedError):
+        model.mmu_generate(idx=idx, remasking="random")
+    with pytest.raises(NotImplementedError):
+        model.mmu_generate(idx=idx, attention_mask=torch.zeros(1, idx.shape[1] + 128, dtype=torch.long))
+    with pytest.raises(AssertionError):
+        model.mmu_generate(idx=idx, max_new_tokens=10, block_length=4)

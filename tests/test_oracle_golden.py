@@ -167,3 +167,18 @@ def test_stepwise_preview_loop_matches_reference_golden(tiny):
             assert [(s, txt, st, im is not None) for s, txt, im, st in ys] == [tuple(y) for y in run["yields"]], run["name"]
             assert [im for _, _, im, _ in ys] == run["overlays"], run["name"]
             assert all(torch.equal(a, b) for a, b in zip(decoded, run["decoded"]))
+
+
+def test_mmu_generate_matches_reference_golden(tiny):
+    """oracle.generate.mmu_generate == MMadaModelLM.mmu_generate (M/models/modeling_mmada.py:619-691) on the tiny model:
+    B=1 two blocks, B=2 with CFG, uneven per-step counts, all-ones attention mask (oracle/make_golden_mmu.py)."""
+    t = load_golden("trajectory_mmu_tiny.pt")
+    model = tiny[3]
+    for run in t["runs"]:
+        am = torch.ones_like(run["out"]) if run["ones_mask"] else None
+        out = G.mmu_generate(model, run["idx"], attention_mask=am, **run["kwargs"])
+        assert torch.equal(out, run["out"]), run["name"]
+    with pytest.raises(NotImplementedError):
+        G.mmu_generate(model, t["runs"][0]["idx"], temperature=0.5)
+    with pytest.raises(NotImplementedError):
+        G.mmu_generate(model, t["runs"][0]["idx"], attention_mask=torch.zeros(1, 152, dtype=torch.long))
