@@ -58,8 +58,9 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* v_empty = bars + 9;   // [2]
     uint64_t* s_full = bars + 11;   // [2]
     uint64_t* p_full = bars + 13;   // [2]
-    uint64_t* pv_done = bars + 15;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* pv_done = bars + 15;  // one phase per PV(j): only the lazy-rescale path waits on it (see there)
+    uint64_t* o_full = bars + 16;   // all PV MMAs retired: the epilogue may read O
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -78,6 +79,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&p_full[s], 4);
         }
         mbar_init(pv_done, 1);
+        mbar_init(o_full, 1);
         fence_barrier_init();
     }
     if (warp == 4) {
@@ -167,6 +169,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     umma_commit(pv_done);
                 }
             }
+            umma_commit(o_full);
         }
         __syncwarp();
     } else {
@@ -213,6 +216,8 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
             if (any_need && j >= 1) {
                 // rare: rescale O (TMEM). PV(j-1) must have retired first; PV(j) cannot start before this P is published.
+                // The parity wait is unambiguous here: S(j) is ready, so QK(j) and everything issued before it (PV(j-2))
+                // has completed - pv_done has finished j-1 or j phases, never fewer.
                 mbar_wait(pv_done, (j - 1) & 1);
                 tcgen05_fence_after();
 #pragma unroll 1
@@ -232,8 +237,10 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[s]);
         }
-        // epilogue: O / l
-        mbar_wait(pv_done, (n_kv - 1) & 1);
+        // epilogue: O / l. Not pv_done: when the last softmax block is done only PV(n_kv-3) is known to have retired, and
+        // a parity wait two phases ahead of the barrier returns at once (it did: rare wrong rows, found by the determinism
+        // check of tests/test_gpu_model.py::test_full_size_properties).
+        mbar_wait(o_full, 0);
         tcgen05_fence_after();
         const int qrow = qt * 128 + r;
         const float inv_l = 1.0f / l_run;

@@ -164,6 +164,30 @@ def test_attention_versions_and_lazy_rescale(version):
         _lib.lib.mmdp_set_attention_version(6)
 
 
+@pytest.mark.parametrize("version", [6, 5, 3])
+def test_attention_bitwise_repeatable(version):
+    """The same attention launch repeated many times at the full sequence length must be bitwise identical. (A parity wait
+    that could return two mbarrier phases early made v6 read O before the last PV MMAs retired - rare, timing dependent,
+    a few query rows per launch; this is the stress that exposes such races.) Two co-resident CTAs per SM, B=2."""
+    from mmada_parallel_b200 import _lib
+    B, L, H = 2, 2414, 16
+    d, M, Lpad = H * 128, 2 * 2414, 2416
+    torch.manual_seed(17)
+    q = bf(torch.randn(M, d, device="cuda"))
+    k = bf(torch.randn(M, d, device="cuda"))
+    vt = torch.zeros(B, H, 128, Lpad, dtype=torch.bfloat16, device="cuda")
+    vt[..., :L] = bf(torch.randn(B, H, 128, L, device="cuda"))
+    _lib.lib.mmdp_set_attention_version(version)
+    try:
+        ref = _lib.attention(q, k, vt, B, H, L, 1.0 / math.sqrt(128.0)).clone()
+        bad = 0
+        for _ in range(150):
+            bad += int(not torch.equal(_lib.attention(q, k, vt, B, H, L, 1.0 / math.sqrt(128.0)), ref))
+        assert bad == 0, f"{bad} of 150 launches differ"
+    finally:
+        _lib.lib.mmdp_set_attention_version(6)
+
+
 def test_rmsnorm_embed_lfq():
     from mmada_parallel_b200 import _lib
     torch.manual_seed(3)
