@@ -79,7 +79,9 @@ MMDP_API int mmdp_qkv_rope_tp(const uint16_t* A, int lda, const uint16_t* Wqkv, 
 MMDP_API int mmdp_resid_add_f32(uint16_t* x, int ldx, const float* partial, int ldp, int M, int d, void* stream);
 
 /* softmax(q k^T * scale) v, no mask, non-causal (F.scaled_dot_product_attention call at modeling_llada.py:672-679).
- * q,k: [B*L, n_heads*128]; vt: [B, n_heads, 128, Lpad]; out: [B*L, n_heads*128]. */
+ * q,k: [B*L, n_heads*128]; vt: [B, n_heads, 128, Lpad]; out: [B*L, n_heads*128]. Lpad >= L, Lpad % 8 == 0; the pad
+ * columns vt[..., L:Lpad] must hold finite values (mmdp_qkv_rope leaves them untouched, mmdp_model_* keeps them zero):
+ * they are multiplied by probabilities that are exactly or nearly (2^-126) zero. */
 MMDP_API int mmdp_attention(const uint16_t* q, const uint16_t* k, const uint16_t* vt, uint16_t* out, int B, int n_heads, int L,
                    int Lpad, float scale, void* stream);
 
