@@ -29,7 +29,7 @@ struct GemmParams {
     int group_m;
 };
 
-__device__ __forceinline__ void gemm_tile_coords(int tl, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+__host__ __device__ __forceinline__ void gemm_tile_coords(int tl, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
     if (group_m <= 0 || group_m >= num_m) {
         m_blk = tl % num_m;
         n_blk = tl / num_m;

@@ -41,6 +41,24 @@ def test_gemm_plain(M, N, K):
     assert_ulp(_lib.gemm_bf16(a, w), ref_linear(a, w), 1, f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M", [5900, 7242])
+def test_gemm_grouped_tile_order(M):
+    """More than 45 m-tiles switch the persistent GEMM to the grouped-M tile order (gemm.cu / gemm_tile_coords): plain and
+    residual epilogues (the latter with its split-K tail) against the fp32 reference, and bit-identical to the plain order."""
+    import os
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(M)
+    K, N = 512, 1024
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    w = bf(torch.randn(N, K, device="cuda") * 0.05)
+    r = bf(torch.randn(M, N, device="cuda"))
+    lin = ref_linear(a, w)
+    got = _lib.gemm_bf16(a, w)
+    assert_ulp(got, lin, 1, f"grouped gemm {M}")
+    assert_ulp(_lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r), bf(lin.float() + r.float()), 2, f"grouped resid {M}", mag=lin)
+    assert torch.equal(got, _lib.gemm_bf16(a, w)), "repeatable"
+
+
 def test_gemm_strided_views():
     """Row-strided A (lda > K) and a row window of W - the restricted LM head uses both."""
     from mmada_parallel_b200 import _lib
