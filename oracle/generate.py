@@ -4,6 +4,8 @@
   interleave_generate  restates MMaDA-Parallel-M/models/modeling_mmada.py:118-248
   generate_ti2ti_stepwise / decode_text_with_masks  restate MMaDA-Parallel-A/app.py:143-398 / :102-140 (Gradio preview loop)
   mmu_generate         restates MMaDA-Parallel-M/models/modeling_mmada.py:619-691 (semi-autoregressive text generation)
+  generate_image       restates MMaDA-Parallel-A/generators/image_generation_generator.py:15-251 (MaskGit T2I; its sampling
+                       helpers are those of A/utils/generation_utils.py:28-61, restated next to it)
 The per-step arithmetic lives in oracle/sampling.py; this file restates the orchestration (schedules, which forwards
 run, how ids are rewritten). The python `.item()` loops of the reference are replaced by tensor indexing with the
 same results. Random draws come from sampling.NoiseSource (same calls, same order as the reference).
@@ -293,3 +295,77 @@ def mmu_generate(model, idx, max_new_tokens=128, steps=128, block_length=128, te
             if trace is not None:
                 trace.append(x.clone())
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A/generators/image_generation_generator.py (T2I MaskGit decoding). No call site in the reference's own scripts; pinned here
+# so that the product path can be built against it next.
+# ---------------------------------------------------------------------------------------------------------------
+def _gumbel_noise_g(t: torch.Tensor, generator=None) -> torch.Tensor:
+    """A/utils/generation_utils.py:28-34: -log(-log(u + 1e-20) + 1e-20), u = torch.rand in t's dtype."""
+    u = torch.rand_like(t) if generator is None else torch.rand(t.shape, device=t.device, dtype=t.dtype, generator=generator)
+    return -torch.log(-torch.log(u + 1e-20) + 1e-20)
+
+
+def _gumbel_max_sample_g(logits: torch.Tensor, tau: float, generator=None) -> torch.Tensor:
+    """generation_utils.py:37-42."""
+    if tau == 0.0:
+        return logits.argmax(dim=-1)
+    return (logits / tau + _gumbel_noise_g(logits, generator)).argmax(dim=-1)
+
+
+def _mask_by_random_topk_g(mask_len: torch.Tensor, probs: torch.Tensor, temperature: float, generator=None) -> torch.Tensor:
+    """generation_utils.py:45-61: True = stay masked; strict `<` against the k-th smallest confidence."""
+    confidence = torch.log(probs.clamp_min(1e-20)) + temperature * _gumbel_noise_g(probs, generator)
+    sorted_conf = torch.sort(confidence, dim=-1).values
+    k = mask_len.long().unsqueeze(1).clamp_(0, probs.size(1) - 1)
+    return confidence < torch.gather(sorted_conf, 1, k)
+
+
+@torch.no_grad()
+def generate_image(model, prompt, *, seq_len=1024, newline_every=16, timesteps=18, mask_token_id=126336, newline_id=126084,
+                   temperature=1.0, cfg_scale=0.0, uncon_ids=None, code_start=None, codebook_size=8192,
+                   noise_schedule=S.cosine_schedule, text_vocab_size=None, generator=None, trace: Optional[list] = None):
+    """Restates generate_image with use_cache=False (the token cache is SURVEY 8f rank 4). `model(ids, infer=True).logits`.
+    Returns LongTensor [1, seq_len] of full-vocabulary ids (VQ id + text_vocab_size), newlines removed (:236-238)."""
+    B, P = prompt.shape
+    assert B == 1, "batch>1 not supported – wrap in loop if needed"                    # :57
+    x = prompt.clone()
+    vq_mask = x == mask_token_id
+    unknown_cnt = vq_mask.sum(dim=1, keepdim=True)
+    vq_len = unknown_cnt
+    if text_vocab_size is None:                                                        # :78-82
+        text_vocab_size = model(torch.zeros(1, 1, dtype=torch.long), infer=True).logits.size(-1) - codebook_size
+    off = text_vocab_size
+    for step in range(timesteps):
+        if int(unknown_cnt) == 0:                                                      # :92
+            break
+        if step < timesteps - 1:                                                       # :99-103
+            frac = noise_schedule(torch.tensor([(step + 1) / timesteps]))
+            keep_n = (vq_len.float() * frac).floor().clamp_min(1).long()
+        else:
+            keep_n = torch.zeros_like(unknown_cnt)
+        if cfg_scale > 0:                                                              # :121-156
+            uncond = torch.cat((uncon_ids, x[:, code_start - 2:]), dim=1)
+            uncond_vq_mask = torch.cat((torch.zeros((1, uncon_ids.size(1)), dtype=torch.bool), vq_mask[:, code_start - 2:]), dim=1)
+            cond_logits = model(x, infer=True).logits[..., off: off + codebook_size]
+            cond_mask_logits = cond_logits[vq_mask].view(B, -1, codebook_size)
+            uncond_logits = model(uncond, infer=True).logits[..., off: off + codebook_size]
+            uncond_mask_logits = uncond_logits[uncond_vq_mask].view(B, -1, codebook_size)
+            logits = (1 + cfg_scale) * cond_mask_logits - cfg_scale * uncond_mask_logits
+        else:
+            logits = model(x, infer=True).logits[:, vq_mask[0], off: off + codebook_size]   # :162
+        sampled = _gumbel_max_sample_g(logits, temperature, generator)                 # :171
+        sampled_full = sampled + off
+        probs = torch.softmax(logits, dim=-1)
+        conf = probs.gather(-1, sampled.unsqueeze(-1)).squeeze(-1)
+        flat_idx = vq_mask.nonzero(as_tuple=False)[:, 1]
+        x.view(-1)[flat_idx] = sampled_full.view(-1)                                   # :189
+        mask_sel = _mask_by_random_topk_g(keep_n.squeeze(1), conf, temperature, generator)   # :204
+        x.view(-1)[flat_idx[mask_sel.view(-1)]] = mask_token_id
+        vq_mask = x == mask_token_id
+        unknown_cnt = vq_mask.sum(dim=1, keepdim=True)
+        if trace is not None:
+            trace.append(dict(step=step, keep_n=int(keep_n), sampled=sampled.clone(), x=x[0].clone()))
+    vq_ids = x[0, code_start:-2]
+    return vq_ids[vq_ids != newline_id].view(1, seq_len)

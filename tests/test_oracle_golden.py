@@ -182,3 +182,19 @@ def test_mmu_generate_matches_reference_golden(tiny):
         G.mmu_generate(model, t["runs"][0]["idx"], temperature=0.5)
     with pytest.raises(NotImplementedError):
         G.mmu_generate(model, t["runs"][0]["idx"], attention_mask=torch.zeros(1, 152, dtype=torch.long))
+
+
+def test_generate_image_t2i_matches_reference_golden(tiny):
+    """oracle.generate.generate_image == A/generators/image_generation_generator.py::generate_image (MaskGit T2I decoding,
+    use_cache=False) on the tiny model: greedy, temperature 1, CFG 3, and an 18-step run that exits early
+    (oracle/make_golden_t2i.py). Groundwork for the product path."""
+    t = load_golden("trajectory_t2i_tiny.pt")
+    model, lay = tiny[3], t["layout"]
+    for run in t["runs"]:
+        tr = []
+        out = G.generate_image(model, lay["prompt"], generator=torch.Generator().manual_seed(run["seed"]), seq_len=lay["seq_len"],
+                               newline_every=lay["newline_every"], code_start=lay["code_start"], uncon_ids=lay["uncon_ids"],
+                               text_vocab_size=126356, codebook_size=8192, trace=tr, **run["kwargs"])
+        assert torch.equal(out, run["vq_ids"]), run["name"]
+        assert len(tr) == run["steps_run"] and out.shape == (1, lay["seq_len"])
+        assert int((out < 126356).sum()) == 0 and int((out >= 126356 + 8192).sum()) == 0
