@@ -115,3 +115,47 @@ def test_gemm_tile_order_is_a_bijection(tmp_path):
                    capture_output=True, timeout=300)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def test_preview_host_helpers_match_oracle():
+    """Host-side pieces of the step-wise preview path (no GPU work): text rendering and image-step schedule equal the pinned
+    oracle; decode_vq_to_image's conversion / overlay / error contract with a stand-in decoder (A/utils/image_utils.py:13-75,
+    A/app.py:312-333)."""
+    from types import SimpleNamespace
+    from oracle import generate as G
+    from mmada_parallel_b200.generators.stepwise import decode_text_with_masks
+    from mmada_parallel_b200.schedule import stepwise_image_step_indices
+    from mmada_parallel_b200.utils.image_utils import decode_vq_to_image, overlay_masked_cells
+    import pytest
+    g = torch.Generator().manual_seed(5)
+    tok = G.PieceTokenizer()
+    for n_mask_runs in range(6):
+        ids = torch.randint(0, 126000, (1, 80), generator=g)
+        for _ in range(n_mask_runs):
+            a = int(torch.randint(0, 70, (1,), generator=g))
+            ids[0, a:a + int(torch.randint(1, 25, (1,), generator=g))] = 126336
+        assert decode_text_with_masks(ids, 5, 75, tok, 126336) == G.decode_text_with_masks(ids, 5, 75, tok, 126336)
+    for T in (3, 10, 64, 100, 128):
+        assert stepwise_image_step_indices(T) == G.stepwise_image_step_indices(T)
+
+    class Dec:  # native decoder protocol: decode_code + decoder.upscale
+        decoder = SimpleNamespace(upscale=16)
+
+        def decode_code(self, ids, shape=None):
+            h, w = shape
+            x = torch.linspace(-1.2, 1.2, 3 * h * 16 * w * 16).view(1, 3, h * 16, w * 16)
+            return x
+    ids = torch.zeros(1, 4, dtype=torch.long)
+    img = decode_vq_to_image(ids, None, None, 32, 32, Dec())
+    want = ((Dec().decode_code(ids, (2, 2))[0] + 1) * 0.5).clamp(0, 1).permute(1, 2, 0).mul(255).round().to(torch.uint8)
+    import numpy as np
+    assert img.size == (32, 32) and np.array_equal(np.asarray(img), want.numpy())
+    over = overlay_masked_cells(img, [1, 2], 2, 16, 16)
+    diff = np.asarray(over).astype(int) - np.asarray(img).astype(int)
+    assert (diff[:16, :16] == 0).all() and (diff[17:, 17:] == 0).all() and (diff[:15, 17:] != 0).any() and (diff[17:, :15] != 0).any()
+    with pytest.raises(ValueError):
+        decode_vq_to_image(torch.zeros(1, 5, dtype=torch.long), None, None, 32, 32, Dec())
+    with pytest.raises(ValueError):
+        decode_vq_to_image(ids, None, None, 32, 32, None)
+    with pytest.raises(TypeError):
+        decode_vq_to_image(ids, None, None, 32, 32, object())
