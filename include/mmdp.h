@@ -49,6 +49,20 @@ MMDP_API void mmdp_set_gemm_pair(int on);
  * 5 = same with 128-wide KV blocks; 3 = O in registers, P through shared memory. Also MMDP_ATTN=3|5|6. Same results up to
  * bf16 rounding of P. */
 MMDP_API void mmdp_set_attention_version(int v);
+/* Split-K tail of the persistent GEMM (csrc/gemm.cu): 0 = never, 1 = residual epilogues only, 2 (default) = every epilogue.
+ * The tiles of a partial last wave are split along K over the idle SMs; partial sums meet in an fp32 workspace owned per
+ * (device, stream) and are reduced in fixed split order, so results are deterministic for a given (M, N, K) but the fp32
+ * summation order of those tiles differs from the unsplit kernel (same bf16 rounding points). Such launches are
+ * cooperative (co-residency of the grid is guaranteed by the runtime). Also MMDP_GEMM_SPLITK. */
+MMDP_API void mmdp_set_gemm_splitk(int mode);
+/* Programmatic dependent launch between the kernels of a forward (1 = default): a kernel's prologue (barrier init,
+ * tensor-memory allocation, descriptor prefetch) overlaps the tail of its predecessor; every kernel waits for the
+ * predecessor's completion (griddepcontrol.wait) before touching its data. Also MMDP_PDL=0|1. */
+MMDP_API void mmdp_set_pdl(int on);
+/* Generic tuning knob (bench/profiling tools): keys "pdl", "gemm_splitk", "gemm_l2pf" (L2 prefetch distance of weight tiles
+ * in k-blocks, 0 = off), "gemm_l2pf_mod", "gemm_pair", "gemm_group_m", "attn_split_tail" (KV-split of attention's partial
+ * last wave), "attn_poly", "rmsnorm_warp". Each defaults to the environment variable MMDP_<KEY in upper case>. */
+MMDP_API int mmdp_set_option(const char* key, int value);
 
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */
 #define MMDP_EPI_PLAIN 0   /* C = bf16(A W^T)                                 nn.Linear, modeling_llada.py:1402      */

@@ -64,6 +64,9 @@ SIGNATURES = {
     "mmdp_launch_count": (C.c_longlong, [_i]),
     "mmdp_set_gemm_pair": (None, [_i]),
     "mmdp_set_attention_version": (None, [_i]),
+    "mmdp_set_gemm_splitk": (None, [_i]),
+    "mmdp_set_pdl": (None, [_i]),
+    "mmdp_set_option": (_i, [C.c_char_p, _i]),
     "mmdp_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "mmdp_qkv_rope": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdp_qkv_rope_tp": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

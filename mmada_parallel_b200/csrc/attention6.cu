@@ -23,6 +23,10 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace mmdp {
 
 static constexpr int k6Threads = 224;  // 4 softmax warps, K producer, MMA issuer, V producer
@@ -40,7 +44,7 @@ template <int POLY>
 __global__ void __launch_bounds__(k6Threads, 2)
 attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
-                    float scale_log2) {
+                    float scale_log2, int n_full, int splits, float* __restrict__ part_ws) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
@@ -63,8 +67,25 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int n_kv = (L + k6BKV - 1) / k6BKV;
+    // work items: [0, n_full) whole (b, h, query tile) problems; then, for each of the remaining tiles (the partial last wave),
+    // `splits` pieces that each cover a slice of the KV blocks and leave an un-normalised partial (O, m, l) in part_ws for
+    // attention_combine_kernel. tile index = (b * H + h) * n_qt + qt.
+    const int n_qt = (L + 127) / 128;
+    const int n_kv_all = (L + k6BKV - 1) / k6BKV;
+    int tile = blockIdx.x, piece = -1;
+    if ((int)blockIdx.x >= n_full) {
+        const int t = (int)blockIdx.x - n_full;
+        tile = n_full + t / splits;
+        piece = t - (t / splits) * splits;
+    }
+    const int qt = tile % n_qt, h = (tile / n_qt) % H, b = tile / (n_qt * H);
+    int jb = 0, je = n_kv_all;
+    if (piece >= 0) {
+        const int per = (n_kv_all + splits - 1) / splits;
+        jb = piece * per;
+        je = (jb + per < n_kv_all) ? jb + per : n_kv_all;
+    }
+    const int n_kv = je - jb;  // >= 1: the host keeps splits <= number of KV blocks / 2
 
     if (warp == 5 && lane == 0) {
         mbar_init(q_full, 1);
@@ -95,6 +116,8 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();  // the prologue above overlaps the tail of the QKV GEMM (programmatic dependent launch)
+    pdl_wait();
     // S[0] cols 0..63, S[1] cols 64..127 (P(j) = packed bf16 pairs in the first 32 columns of S[j & 1]), O cols 128..255
     const uint32_t tS0 = tmem_base, tO = tmem_base + 128;
 
@@ -108,7 +131,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             int st = 0;
             uint32_t ph = 0;
             for (int j = 0; j < n_kv; ++j) {
-                const int kv0 = j * k6BKV;
+                const int kv0 = (jb + j) * k6BKV;
                 mbar_wait(&k_empty[st], ph ^ 1);
                 mbar_expect_tx(&k_full[st], k6KBytes);
                 tma_load_2d(sK + st * k6KBytes, &tmK, &k_full[st], h * 128, b * L + kv0);
@@ -124,7 +147,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const int st = j & 1;
                 mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&v_full[st], k6VBytes);
-                tma_load_2d(sV + st * k6VBytes, &tmVt, &v_full[st], j * k6BKV, (b * H + h) * 128);
+                tma_load_2d(sV + st * k6VBytes, &tmVt, &v_full[st], (jb + j) * k6BKV, (b * H + h) * 128);
             }
         }
         __syncwarp();
@@ -181,7 +204,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         for (int j = 0; j < n_kv; ++j) {
             const int s = j & 1;
-            const int nvalid = L - j * k6BKV;
+            const int nvalid = L - (jb + j) * k6BKV;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tcgen05_fence_after();
             uint32_t sv[64];
@@ -243,20 +266,40 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(o_full, 0);
         tcgen05_fence_after();
         const int qrow = qt * 128 + r;
-        const float inv_l = 1.0f / l_run;
-        __nv_bfloat16* orow = out + (size_t)(b * L + (qrow < L ? qrow : 0)) * d_model + h * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
-            tmem_ld_wait();
+        if (piece >= 0) {
+            // partial result of this KV slice: O un-normalised (scaled by 2^(-m_used c)), m_used, l - merged by the combine kernel
+            float* slot = part_ws + (size_t)((tile - n_full) * splits + piece) * (128 * 128 + 256);
             if (qrow < L) {
-                uint32_t o[16];
+                slot[128 * 128 + r] = m_used;
+                slot[128 * 128 + 128 + r] = l_run;
+            }
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
+                tmem_ld_wait();
+                if (qrow < L) {
+                    uint4* d4 = reinterpret_cast<uint4*>(slot + (size_t)r * 128 + c * 32);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
-                uint4* d4 = reinterpret_cast<uint4*>(orow + c * 32);
+                    for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        } else {
+            const float inv_l = 1.0f / l_run;
+            __nv_bfloat16* orow = out + (size_t)(b * L + (qrow < L ? qrow : 0)) * d_model + h * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
+                tmem_ld_wait();
+                if (qrow < L) {
+                    uint32_t o[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
+                    uint4* d4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
             }
         }
     }
@@ -269,6 +312,50 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
 }
 
+// Merges the `splits` KV-slice partials of one split tile: out = (sum_i w_i O_i) / (sum_i w_i l_i), w_i = 2^((m_i - m) c).
+// One CTA per (split tile, query row), thread = output column.
+__global__ void __launch_bounds__(128)
+attention_combine_kernel(const float* __restrict__ part_ws, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
+                         float scale_log2, int n_full, int splits) {
+    const int n_qt = (L + 127) / 128;
+    const int st = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tile = n_full + st;
+    const int qt = tile % n_qt, h = (tile / n_qt) % H, b = tile / (n_qt * H);
+    const int qrow = qt * 128 + r;
+    if (qrow >= L) return;
+    const float* base = part_ws + (size_t)st * splits * (128 * 128 + 256);
+    float m = -INFINITY;
+    for (int i = 0; i < splits; ++i) m = fmaxf(m, base[(size_t)i * (128 * 128 + 256) + 128 * 128 + r]);
+    float o = 0.f, l = 0.f;
+    for (int i = 0; i < splits; ++i) {
+        const float* slot = base + (size_t)i * (128 * 128 + 256);
+        const float w = exp2f((slot[128 * 128 + r] - m) * scale_log2);
+        o = fmaf(w, slot[(size_t)r * 128 + c], o);
+        l = fmaf(w, slot[128 * 128 + 128 + r], l);
+    }
+    out[(size_t)(b * L + qrow) * d_model + h * 128 + c] = __float2bfloat16_rn(o / l);
+}
+
+// KV-slice partials of the split tail: one buffer per (device, stream), grown on demand
+static std::map<std::pair<int, cudaStream_t>, std::pair<float*, size_t>> g_attn_ws;
+static std::mutex g_attn_ws_mu;
+static int attn_part_workspace(cudaStream_t stream, size_t need, float** out) {
+    int dev = 0;
+    MMDP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_attn_ws_mu);
+    auto& e = g_attn_ws[std::make_pair(dev, stream)];
+    if (need > e.second) {
+        if (e.first) MMDP_CUDA(cudaFree(e.first));  // synchronises with the launches that still read it
+        e.first = nullptr; e.second = 0;
+        MMDP_CUDA(cudaMalloc(&e.first, need));
+        e.second = need;
+    }
+    *out = e.first;
+    return 0;
+}
+
 int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
                      int Lpad, float scale, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || L <= 0) return set_error("attention: empty problem");
@@ -279,19 +366,40 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     if (make_tmap_2d_bf16(&tmK, k, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, k6BKV, 64)) return -1;
     if (make_tmap_2d_bf16(&tmVt, vt, (uint64_t)B * H * 128, (uint64_t)Lpad, (uint64_t)Lpad, 128, 64)) return -1;
     // share of exp2 evaluated on the FMA pipe: every POLY-th pair's second element (0 = none; default 4 = 1/8 of all exp2). MMDP_ATTN_POLY = 0|2|4|8.
-    static int poly = -1;
-    if (poly < 0) {
-        const char* e = getenv("MMDP_ATTN_POLY");
-        poly = e ? atoi(e) : 4;  // measured 914 / 916 / 925 / 889 TFLOP/s for 0 / 8 / 4 / 2 (B=1, L=2414, H=32)
-        if (poly != 0 && poly != 2 && poly != 8) poly = 4;
+    int poly = opt(OPT_ATTN_POLY);  // measured 914 / 916 / 925 / 889 TFLOP/s for 0 / 8 / 4 / 2 (B=1, L=2414, H=32)
+    if (poly != 0 && poly != 2 && poly != 8) poly = 4;
+    const int split_tail = opt(OPT_ATTN_SPLIT_TAIL);
+    // Partial last wave: tiles % (2 CTAs x SMs) leftover tiles would run alone at the end (608 tiles on 296 slots: 30 % of the
+    // launch at B=1). Split their KV range over the idle slots and merge the partials (attention_combine_kernel).
+    const int n_qt = (L + 127) / 128, n_kvb = (L + k6BKV - 1) / k6BKV;
+    const int tiles = n_qt * H * B, slots = 2 * num_sms();
+    int n_full = tiles, n_split = 0, splits = 1;
+    if (split_tail && tiles > slots && (tiles % slots) > 0 && (tiles % slots) * 4 <= slots) {
+        n_split = tiles % slots;
+        splits = slots / n_split;
+        if (splits > 8) splits = 8;
+        if (splits > n_kvb / 2) splits = n_kvb / 2;
+        // no empty piece: piece i covers KV blocks [i * per, (i + 1) * per) with per = ceil(n_kvb / splits)
+        while (splits >= 2 && (splits - 1) * ((n_kvb + splits - 1) / splits) >= n_kvb) --splits;
+        if (splits >= 2) n_full = tiles - n_split; else { n_split = 0; splits = 1; }
     }
-    dim3 grid((L + 127) / 128, H, B);
+    float* part_ws = nullptr;
+    if (n_split > 0 && attn_part_workspace(stream, (size_t)n_split * splits * (128 * 128 + 256) * sizeof(float), &part_ws)) return -1;
+    const int grid = n_full + n_split * splits;
     const float scale_log2 = scale * 1.4426950408889634f;
+    const bool pdl = pdl_mode() != 0;
     LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)L * L * 128, stream);
     auto launch = [&](auto kernel) -> int {
-        MMDP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k6Smem));
-        MMDP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        kernel<<<grid, k6Threads, k6Smem, stream>>>(tmQ, tmK, tmVt, out, H, L, d_model, scale_log2);
+        static unsigned long long attr_set = 0;  // bit per device (one instantiation per POLY value)
+        int dev = 0;
+        MMDP_CUDA(cudaGetDevice(&dev));
+        if (!(attr_set >> (dev & 63) & 1ull)) {
+            MMDP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k6Smem));
+            MMDP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_set |= 1ull << (dev & 63);
+        }
+        MMDP_CUDA(launch_ex(kernel, dim3(grid), dim3(k6Threads), k6Smem, stream, pdl, false, tmQ, tmK, tmVt, out, H, L, d_model,
+                            scale_log2, n_full, splits, part_ws));
         return 0;
     };
     if (poly == 2) { if (launch(attention_v6_kernel<2>)) return -1; }
@@ -299,6 +407,9 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     else if (poly == 8) { if (launch(attention_v6_kernel<8>)) return -1; }
     else { if (launch(attention_v6_kernel<0>)) return -1; }
     MMDP_CUDA(cudaGetLastError());
+    if (n_split > 0)
+        MMDP_CUDA(launch_ex(attention_combine_kernel, dim3(n_split, 128), dim3(128), 0, stream, pdl, false, (const float*)part_ws, out, H, L,
+                            d_model, scale_log2, n_full, splits));
     return 0;
 }
 

@@ -11,6 +11,8 @@ namespace mmdp {
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ wte,
                              __nv_bfloat16* __restrict__ x, int d, int64_t vocab) {
     const int row = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     int64_t id = ids[row];
     if (id < 0 || id >= vocab) id = 0;  // torch would raise; ids are validated on the host, this only avoids OOB reads
     const uint4* src = reinterpret_cast<const uint4*>(wte + (size_t)id * d);
@@ -22,8 +24,7 @@ int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, i
                cudaStream_t stream) {
     if (d % 8) return set_error("embed: d must be a multiple of 8");
     LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read row + write row
-    embed_kernel<<<M, 128, 0, stream>>>(ids, wte, x, d, vocab);
-    MMDP_CUDA(cudaGetLastError());
+    MMDP_CUDA(launch_ex(embed_kernel, dim3(M), dim3(128), 0, stream, pdl_mode() != 0, false, ids, wte, x, d, vocab));
     return 0;
 }
 
@@ -32,6 +33,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int d, float eps) {
     const int orow = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int irow = rows ? rows[orow] : orow;
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)irow * ldx);
     const uint4* w4 = reinterpret_cast<const uint4*>(w);
@@ -114,6 +117,8 @@ __global__ void __launch_bounds__(256, 2)
 rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
                     const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int M, float eps) {
     const int orow = blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
     if (orow >= M) return;
     const int lane = threadIdx.x & 31;
     const int irow = rows ? rows[orow] : orow;
@@ -178,19 +183,18 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
     if ((d % 8) || (ldx % 8) || (ldy % 8)) return set_error("rmsnorm: d/ldx/ldy must be multiples of 8");
     LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read x + write y
     const int grid8 = (M + 7) / 8;
-    static int use_warp = -1;
-    if (use_warp < 0) {
-        const char* e = getenv("MMDP_RMSNORM_WARP");
-        use_warp = (e && e[0] == '0') ? 0 : 1;
-    }
+    const int use_warp = opt(OPT_RMSNORM_WARP);
+    const bool pdl = pdl_mode() != 0;
+    cudaError_t e;
     switch (use_warp ? d : -1) {  // warp-per-row variants for the model widths in use; anything else takes the CTA-per-row kernel
-        case 4096: rmsnorm_warp_kernel<16><<<grid8, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, M, eps); break;
-        case 2048: rmsnorm_warp_kernel<8><<<grid8, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, M, eps); break;
-        case 1024: rmsnorm_warp_kernel<4><<<grid8, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, M, eps); break;
-        case 512: rmsnorm_warp_kernel<2><<<grid8, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, M, eps); break;
-        case 256: rmsnorm_warp_kernel<1><<<grid8, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, M, eps); break;
-        default: rmsnorm_kernel<<<M, 256, 0, stream>>>(x, ldx, rows, w, y, ldy, d, eps);
+        case 4096: e = launch_ex(rmsnorm_warp_kernel<16>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
+        case 2048: e = launch_ex(rmsnorm_warp_kernel<8>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
+        case 1024: e = launch_ex(rmsnorm_warp_kernel<4>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
+        case 512: e = launch_ex(rmsnorm_warp_kernel<2>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
+        case 256: e = launch_ex(rmsnorm_warp_kernel<1>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
+        default: e = launch_ex(rmsnorm_kernel, dim3(M), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, d, eps);
     }
+    MMDP_CUDA(e);
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -200,6 +204,8 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
 __global__ void __launch_bounds__(256) resid_add_f32_kernel(__nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ part,
                                                              int ldp, int d) {
     const int row = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     uint4* xr = reinterpret_cast<uint4*>(x + (size_t)row * ldx);
     const float4* pr = reinterpret_cast<const float4*>(part + (size_t)row * ldp);
     for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
@@ -218,8 +224,7 @@ int resid_add_f32(__nv_bfloat16* x, int ldx, const float* partial, int ldp, int 
     if (M <= 0) return 0;
     if ((d % 8) || (ldx % 8) || (ldp % 4)) return set_error("resid_add_f32: d/ldx must be multiples of 8, ldp of 4");
     LaunchScope ls(LK_ROW, (double)M * d * 8, stream);
-    resid_add_f32_kernel<<<M, 256, 0, stream>>>(x, ldx, partial, ldp, d);
-    MMDP_CUDA(cudaGetLastError());
+    MMDP_CUDA(launch_ex(resid_add_f32_kernel, dim3(M), dim3(256), 0, stream, pdl_mode() != 0, false, x, ldx, partial, ldp, d));
     return 0;
 }
 

@@ -15,6 +15,10 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace mmdp {
 
 static constexpr int BM = 128, BK = 64;
@@ -67,6 +71,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above overlaps the tail of the previous kernel in the stream (programmatic dependent launch)
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int num_m = (p.M + BM - 1) / BM;
     const int num_n = (p.N + BN - 1) / BN;
@@ -93,7 +100,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int m_blk, n_blk;
                 gemm_tile_coords(tl, num_m, num_n, p.group_m, m_blk, n_blk);
                 const int kb_beg = is_unit ? unit_kb0 : 0, kb_end = is_unit ? unit_kb1 : num_k;
+                // weight tiles are prefetched into L2 `l2pf` k-blocks ahead by every l2pf_mod-th m-tile's CTA (the CTAs that
+                // share an n-tile run in lock-step, so one of them fetching ahead turns the others' DRAM misses into L2 hits)
+                const bool pf = p.l2pf > 0 && ((m_blk + n_blk) % p.l2pf_mod) == 0;
                 for (int kb = kb_beg; kb < kb_end; ++kb) {
+                    if (pf && kb + p.l2pf < kb_end) tma_prefetch_l2_2d(&tmB, (kb + p.l2pf) * BK, n_blk * BN);
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], kStageBytes);
                     uint8_t* sa = smem + s * kStageBytes;
@@ -157,60 +168,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             bool run_epilogue = true;
             if (is_unit) {
                 run_epilogue = false;
-                if constexpr (EPI == EPI_RESID) {
-                    // (1) publish this unit's partial accumulator (fp32, [128][BN])
-                    const int rit = ew * 32 + lane;  // row in tile
-                    float* my = p.sk_ws + ((size_t)(unit_t * p.sk_splits + unit_s) * BM + rit) * BN;
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tbase + c * 32, v);
-                        tmem_ld_wait();
-                        uint4* d4 = reinterpret_cast<uint4*>(my + c * 32);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                const int S = p.sk_splits;
+                const int rit = ew * 32 + lane;  // row in tile == TMEM lane of this thread
+                float4* tile_ws = reinterpret_cast<float4*>(p.sk_ws) + (size_t)unit_t * S * (BN / 4) * BM;
+                // (1) publish this unit's partial accumulator
+                sk_publish<BN>(tile_ws + (size_t)unit_s * (BN / 4) * BM, tbase, rit);
+                __threadfence();
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps
+                // (2) wait until every unit of this tile has published. All units are co-resident: the launch is cooperative
+                //     (grid <= SMs x 1 CTA/SM is checked by the runtime), so a unit can only wait for CTAs that are running.
+                if (rit == 0) {
+                    atomicAdd(p.sk_cnt + 2 * unit_t, 1);
+                    uint32_t spins = 0;
+                    while (*reinterpret_cast<volatile int*>(p.sk_cnt + 2 * unit_t) < S) {
+                        if (++spins > (1u << 26)) { printf("mmdp: split-K wait timeout tile %d\n", unit_t); __trap(); }
                     }
                     __threadfence();
-                    asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps
-                    // (2) wait until every unit of this tile has published (all units are co-resident: one CTA per SM)
-                    if (ew == 0 && lane == 0) {
-                        atomicAdd(p.sk_cnt + 2 * unit_t, 1);
-                        uint32_t spins = 0;
-                        while (*reinterpret_cast<volatile int*>(p.sk_cnt + 2 * unit_t) < p.sk_splits) {
-                            if (++spins > (1u << 26)) { printf("mmdp: split-K wait timeout tile %d\n", unit_t); __trap(); }
-                        }
-                        __threadfence();
-                    }
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
-                    // (3) distributed reduction + residual epilogue: this unit owns 1/splits of the tile's float4 groups.
-                    //     Partials are summed in split order 0..S-1 (deterministic), then bf16(bf16(sum) + resid).
-                    const int groups = BM * BN / 4;
-                    const int per = (groups + p.sk_splits - 1) / p.sk_splits;
-                    const int g0 = unit_s * per, g1 = (g0 + per < groups) ? g0 + per : groups;
-                    const float* tbase_ws = p.sk_ws + (size_t)unit_t * p.sk_splits * BM * BN;
-                    const int tid = ew * 32 + lane;
-                    for (int g = g0 + tid; g < g1; g += 128) {
-                        const int rr = (g * 4) / BN, cc = (g * 4) - rr * BN;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int sp = 0; sp < p.sk_splits; ++sp) {
-                            const float4 t = __ldcg(reinterpret_cast<const float4*>(tbase_ws + ((size_t)sp * BM + rr) * BN + cc));
-                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                        }
-                        const int grow = m_blk * BM + rr, gcol = n_blk * BN + cc;
-                        if (grow < p.M && gcol < p.N) {
-                            const uint2 rv = *reinterpret_cast<const uint2*>(p.resid + (size_t)grow * p.ldr + gcol);
-                            uint2 o;
-                            o.x = pack_bf16x2(__fadd_rn(bf16_lo(rv.x), bf16_round(acc.x)), __fadd_rn(bf16_hi(rv.x), bf16_round(acc.y)));
-                            o.y = pack_bf16x2(__fadd_rn(bf16_lo(rv.y), bf16_round(acc.z)), __fadd_rn(bf16_hi(rv.y), bf16_round(acc.w)));
-                            *reinterpret_cast<uint2*>(p.C + (size_t)grow * p.ldc + gcol) = o;
-                        }
-                    }
-                    // (4) the last unit to finish re-arms the counters for the next launch
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
-                    if (ew == 0 && lane == 0) {
-                        const int old = atomicAdd(p.sk_cnt + 2 * unit_t + 1, 1);
-                        if (old == p.sk_splits - 1) { p.sk_cnt[2 * unit_t] = 0; p.sk_cnt[2 * unit_t + 1] = 0; }
-                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                // (3) distributed reduction + fused epilogue on the rows this unit owns (gemm_epilogue.cuh)
+                sk_finish<EPI, BN>(p, tile_ws, S, unit_s, m_blk, n_blk, rit);
+                // (4) the last unit to finish re-arms the counters for the next launch
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (rit == 0) {
+                    const int old = atomicAdd(p.sk_cnt + 2 * unit_t + 1, 1);
+                    if (old == S - 1) { p.sk_cnt[2 * unit_t] = 0; p.sk_cnt[2 * unit_t + 1] = 0; }
                 }
             }
             if (run_epilogue) gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk);
@@ -234,34 +216,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static bool g_coop_pdl_ok = true;  // cleared if the driver rejects cooperative + programmatic launch together
+
 template <int EPI, int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;  // bit per device
+    int dev = 0;
+    MMDP_CUDA(cudaGetDevice(&dev));
+    if (!(attr_set >> (dev & 63) & 1ull)) {
         MMDP_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmem));
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_bf16_kernel<EPI, BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, stream>>>(tmA, tmB, p);
+    // A launch with a split-K tail spin-waits between CTAs -> cooperative launch (the runtime guarantees co-residency of
+    // the whole grid or fails the launch; a plain launch could hang behind a concurrent kernel that holds SMs).
+    const bool coop = p.sk_tail > 0;
+    const bool pdl = pdl_mode() != 0;
+    cudaError_t e = launch_ex(gemm_bf16_kernel<EPI, BN>, dim3(grid), dim3(kGemmThreads), GemmCfg<BN>::kSmem, stream,
+                              pdl && (!coop || g_coop_pdl_ok), coop, tmA, tmB, p);
+    if (e != cudaSuccess && coop && pdl && g_coop_pdl_ok) {
+        (void)cudaGetLastError();
+        g_coop_pdl_ok = false;
+        e = launch_ex(gemm_bf16_kernel<EPI, BN>, dim3(grid), dim3(kGemmThreads), GemmCfg<BN>::kSmem, stream, false, true, tmA, tmB, p);
+    }
+    if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }
 
 // Launch plan: tile width (256 | 192), grid, and the split-K tail. Cost model = tile width x (full waves + tail), where a
 // split tail costs 1/splits of a wave plus the partial-sum exchange. Split-K changes the fp32 summation ORDER of the
-// affected tiles (not the rounding points), so it is enabled only for the residual GEMMs of the transformer body
-// (whose shapes are the same in every forward of a run) and can be disabled with MMDP_GEMM_SPLITK=0.
+// affected tiles (not the rounding points); which tiles are affected depends on (M, N, K) only, so results are
+// deterministic for a given problem shape. MMDP_GEMM_SPLITK: 0 = never, 1 = residual GEMMs only (round-1 behaviour),
+// 2 (default) = every epilogue.
 struct GemmPlan { int bn, grid, tail, splits, kb_per; };
-static int g_splitk_mode = -1;
+int gemm_splitk_mode() { return opt(OPT_GEMM_SPLITK); }
+void set_gemm_splitk_mode(int m) { set_opt("gemm_splitk", m); }
+
 static GemmPlan plan_gemm(int epi, int M, int N, int K) {
-    if (g_splitk_mode < 0) {
-        const char* e = getenv("MMDP_GEMM_SPLITK");
-        g_splitk_mode = (e && e[0] == '0') ? 0 : 1;
-    }
+    const int mode = gemm_splitk_mode();
     const int g = num_sms();
     const int num_k = (K + BK - 1) / BK;
     const bool flexible = epi == EPI_PLAIN || epi == EPI_RESID || epi == EPI_F32;
-    const bool may_split = g_splitk_mode && epi == EPI_RESID && num_k >= 4;
+    const bool may_split = num_k >= 4 && (mode >= 2 || (mode == 1 && epi == EPI_RESID));
     GemmPlan best{256, 0, 0, 0, 0};
     double best_cost = 1e30;
     for (int bn : {256, 192}) {
@@ -275,12 +272,19 @@ static GemmPlan plan_gemm(int epi, int M, int N, int K) {
         if (may_split && tail > 0 && tail * 2 <= g) {
             int splits = g / tail;
             if (splits > num_k / 2) splits = num_k / 2;
+            if (splits > kSkMaxSplits) splits = kSkMaxSplits;
             if (splits >= 2) {
                 const int kb_per = (num_k + splits - 1) / splits;
                 splits = (num_k + kb_per - 1) / kb_per;
-                pl.tail = tail; pl.splits = splits; pl.kb_per = kb_per;
-                pl.grid = full > 0 ? g : tail * splits;
-                waves = (double)(full / g) + (double)kb_per / num_k + 0.10;
+                // exchange cost in units of one tile's main loop: publish + finish move 2 x 128 KB per unit through L2
+                // (~4 us) against num_k x ~0.3 us of MMA time
+                const double exch = 12.0 / num_k + 0.04;
+                const double split_waves = (double)(full / g) + (double)kb_per / num_k + exch;
+                if (split_waves < waves) {
+                    pl.tail = tail; pl.splits = splits; pl.kb_per = kb_per;
+                    pl.grid = full > 0 ? g : tail * splits;
+                    waves = split_waves;
+                }
             }
         }
         const double cost = waves * bn * (bn == 192 ? 1.04 : 1.0);
@@ -289,26 +293,30 @@ static GemmPlan plan_gemm(int epi, int M, int N, int K) {
     return best;
 }
 
-static float* g_sk_ws = nullptr;
-static int* g_sk_cnt = nullptr;
-static int ensure_splitk_workspace() {
-    if (g_sk_ws) return 0;
+// Split-K workspace: one per (device, stream) - two streams running split GEMMs at the same time must not share partial
+// sums or arrival counters. 148 units x 128 KB + counters, allocated on first use, kept for the life of the process.
+struct SkWorkspace { float* ws; int* cnt; };
+static std::map<std::pair<int, cudaStream_t>, SkWorkspace> g_sk;
+static std::mutex g_sk_mu;
+static int splitk_workspace(cudaStream_t stream, SkWorkspace* out) {
+    int dev = 0;
+    MMDP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_sk_mu);
+    auto key = std::make_pair(dev, stream);
+    auto it = g_sk.find(key);
+    if (it != g_sk.end()) { *out = it->second; return 0; }
     const size_t units = 256;  // >= number of SMs
-    MMDP_CUDA(cudaMalloc(&g_sk_ws, units * BM * 256 * sizeof(float)));
-    MMDP_CUDA(cudaMalloc(&g_sk_cnt, 2 * units * sizeof(int)));  // [tile][arrived, finished]
-    MMDP_CUDA(cudaMemset(g_sk_cnt, 0, 2 * units * sizeof(int)));
+    SkWorkspace w{nullptr, nullptr};
+    MMDP_CUDA(cudaMalloc(&w.ws, units * BM * 256 * sizeof(float)));
+    MMDP_CUDA(cudaMalloc(&w.cnt, 2 * units * sizeof(int)));  // [tile][arrived, finished]
+    MMDP_CUDA(cudaMemsetAsync(w.cnt, 0, 2 * units * sizeof(int), stream));
+    g_sk.emplace(key, w);
+    *out = w;
     return 0;
 }
 
-static int g_pair_mode = -1;
-int gemm_pair_mode() {
-    if (g_pair_mode < 0) {
-        const char* e = getenv("MMDP_GEMM_PAIR");
-        g_pair_mode = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
-    }
-    return g_pair_mode;
-}
-void set_gemm_pair_mode(int on) { g_pair_mode = (on == 2) ? 2 : (on ? 1 : 0); }
+int gemm_pair_mode() { return opt(OPT_GEMM_PAIR); }
+void set_gemm_pair_mode(int on) { set_opt("gemm_pair", (on == 2) ? 2 : (on ? 1 : 0)); }
 
 int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa,
@@ -354,11 +362,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     // of a caller that batches its CFG branches): +4..7 % on every body GEMM shape, DRAM reads 668 -> 362 MB; no gain below
     // ~45 m-tiles, so M = 2414 keeps the plain order (profiles/r01/README.md). MMDP_GEMM_GROUP_M overrides: 0 = off, n > 0 =
     // fixed group size.
-    static int group_m_env = -2;
-    if (group_m_env == -2) {
-        const char* e = getenv("MMDP_GEMM_GROUP_M");
-        group_m_env = e ? atoi(e) : -1;
-    }
+    const int group_m_env = opt(OPT_GEMM_GROUP_M);
     {
         const int num_m = (M + BM - 1) / BM;
         int g = 0;
@@ -369,8 +373,14 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
         p.group_m = group_m_env >= 0 ? group_m_env : g;
     }
     if (pl.tail > 0) {
-        if (ensure_splitk_workspace()) return -1;
-        p.sk_tail = pl.tail; p.sk_splits = pl.splits; p.sk_kb_per = pl.kb_per; p.sk_ws = g_sk_ws; p.sk_cnt = g_sk_cnt;
+        SkWorkspace w;
+        if (splitk_workspace(stream, &w)) return -1;
+        p.sk_tail = pl.tail; p.sk_splits = pl.splits; p.sk_kb_per = pl.kb_per; p.sk_ws = w.ws; p.sk_cnt = w.cnt;
+    }
+    {
+        // L2 prefetch of weight tiles: MMDP_GEMM_L2PF = distance in k-blocks (0 = off), MMDP_GEMM_L2PF_MOD = every n-th m-tile
+        p.l2pf = opt(OPT_GEMM_L2PF);
+        p.l2pf_mod = opt(OPT_GEMM_L2PF_MOD) < 1 ? 1 : opt(OPT_GEMM_L2PF_MOD);
     }
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;

@@ -27,6 +27,43 @@ void prof_enable(int on);
 int prof_summary(double* ms, double* work, long long* launches);  // arrays of LK_COUNT; synchronises the device
 long long launch_count(int reset);
 
+// Launch options of the library (runtime.cu). pdl: consecutive kernels of a forward are launched with programmatic
+// stream serialization (MMDP_PDL=0 disables); every kernel launched through launch_ex with pdl=true calls pdl_wait().
+int pdl_mode();
+void set_pdl_mode(int on);
+int env_int(const char* name, int dflt);
+// tuning options (runtime.cu): environment default, mmdp_set_option(key, value) at run time
+enum OptId { OPT_PDL = 0, OPT_GEMM_SPLITK, OPT_GEMM_L2PF, OPT_GEMM_L2PF_MOD, OPT_GEMM_PAIR, OPT_GEMM_GROUP_M, OPT_ATTN_SPLIT_TAIL,
+             OPT_ATTN_POLY, OPT_RMSNORM_WARP, OPT_COUNT };
+int opt(int id);
+int set_opt(const char* key, int value);
+
+// cudaLaunchKernelEx wrapper: optional programmatic dependent launch and/or cooperative (co-residency guaranteed) launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                             bool coop, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (coop) {
+        at[n].id = cudaLaunchAttributeCooperative;
+        at[n].val.cooperative = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define MMDP_CUDA(expr)                                                                              \
     do {                                                                                             \
         cudaError_t _e = (expr);                                                                     \
@@ -75,6 +112,8 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
                    __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa, cudaStream_t stream);
 int gemm_pair_mode();
 void set_gemm_pair_mode(int on);
+int gemm_splitk_mode();
+void set_gemm_splitk_mode(int mode);
 
 // attention kernel selection: 4 (default, attention4.cu) or 3 (attention.cu); also MMDP_ATTN=3
 void set_attention_version(int v);

@@ -90,6 +90,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// L2 prefetch of a tile (no shared-memory destination, no barrier): hides the DRAM latency of a tile several k-blocks
+// ahead without spending shared-memory stages on it.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (griddepcontrol). A kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has
+// completed and its memory is visible (no-op for an ordinary launch). Everything before it must not touch global memory
+// the predecessor writes. pdl_launch_dependents() lets the successor's CTAs be scheduled as resources free up; it is
+// issued AFTER tensor memory has been allocated, so a successor CTA can never take the TMEM columns a not-yet-started
+// CTA of this grid needs.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------

@@ -4,8 +4,11 @@
 #include "mmdp_internal.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace mmdp {
@@ -31,6 +34,37 @@ int num_sms() {
     }
     return n;
 }
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+// Tuning options: initialised from the environment on first use, changeable at run time with mmdp_set_option().
+struct Opt { const char* key; const char* env; int dflt; int val; bool init; };
+static Opt g_opts[OPT_COUNT] = {
+    {"pdl", "MMDP_PDL", 1, 0, false},
+    {"gemm_splitk", "MMDP_GEMM_SPLITK", 2, 0, false},
+    {"gemm_l2pf", "MMDP_GEMM_L2PF", 0, 0, false},
+    {"gemm_l2pf_mod", "MMDP_GEMM_L2PF_MOD", 4, 0, false},
+    {"gemm_pair", "MMDP_GEMM_PAIR", 0, 0, false},
+    {"gemm_group_m", "MMDP_GEMM_GROUP_M", -1, 0, false},
+    {"attn_split_tail", "MMDP_ATTN_SPLIT_TAIL", 1, 0, false},
+    {"attn_poly", "MMDP_ATTN_POLY", 4, 0, false},
+    {"rmsnorm_warp", "MMDP_RMSNORM_WARP", 1, 0, false},
+};
+int opt(int id) {
+    Opt& o = g_opts[id];
+    if (!o.init) { o.val = env_int(o.env, o.dflt); o.init = true; }
+    return o.val;
+}
+int set_opt(const char* key, int value) {
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(g_opts[i].key, key)) { g_opts[i].val = value; g_opts[i].init = true; return 0; }
+    return set_error("mmdp_set_option: unknown option '%s'", key);
+}
+int pdl_mode() { return opt(OPT_PDL) ? 1 : 0; }
+void set_pdl_mode(int on) { set_opt("pdl", on ? 1 : 0); }
 
 // ------------------------------------------------------------------------------------------------
 // launch accounting / profiling
@@ -101,6 +135,30 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return make_tmap_2d(out, base, 2, rows, cols, ld, box_rows, box_cols);
 }
 
+// Encoded tensor maps are cached per (base, shape, stride, box): a forward re-uses the same ~10 buffers x ~130 weight
+// matrices on every call, and cuTensorMapEncodeTiled costs ~1-2 us of host time per call (2-3 per GEMM / attention launch).
+struct TmapKey {
+    const void* base;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows, box_cols;
+    int elem_bytes;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols && elem_bytes == o.elem_bytes;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+        h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+        h ^= (k.ld + ((uint64_t)k.box_rows << 32) + ((uint64_t)k.box_cols << 8) + (uint64_t)k.elem_bytes + (h << 6) + (h >> 2));
+        return (size_t)h;
+    }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols) {
     EncodeTiledFn fn = encode_fn();
@@ -108,6 +166,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
     if (elem_bytes != 2 && elem_bytes != 4) return set_error("tmap: element size must be 2 (bf16) or 4 (fp32)");
     if (box_cols * (uint32_t)elem_bytes != 128) return set_error("tmap: box must be exactly one 128-byte swizzle atom wide");
     if (box_rows == 0 || box_rows > 256) return set_error("tmap: box_rows out of range");
+    const TmapKey key{base, rows, cols, ld, box_rows, box_cols, elem_bytes};
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        auto it = g_tmaps.find(key);
+        if (it != g_tmaps.end()) {
+            *out = it->second;
+            return 0;
+        }
+    }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {ld * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
@@ -119,6 +186,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
         return set_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%llu cols=%llu ld=%llu box=[%u,%u]", (int)r,
                          base, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows,
                          box_cols);
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        if (g_tmaps.size() >= 8192) g_tmaps.clear();  // bounded: callers with ever-changing buffers just re-encode
+        g_tmaps.emplace(key, *out);
+    }
     return 0;
 }
 
