@@ -49,7 +49,8 @@ MMDP_API void mmdp_set_gemm_pair(int on);
  * 5 = same with 128-wide KV blocks; 3 = O in registers, P through shared memory. Also MMDP_ATTN=3|5|6. Same results up to
  * bf16 rounding of P. */
 MMDP_API void mmdp_set_attention_version(int v);
-/* Split-K tail of the persistent GEMM (csrc/gemm.cu): 0 = never, 1 = residual epilogues only, 2 (default) = every epilogue.
+/* Split-K tail of the persistent GEMM (csrc/gemm.cu): 0 = never, 1 = residual epilogues only, 2 (default) = every epilogue
+ * where the launch planner's cost model says it pays, 3 = whenever a partial last wave exists (tests).
  * The tiles of a partial last wave are split along K over the idle SMs; partial sums meet in an fp32 workspace owned per
  * (device, stream) and are reduced in fixed split order, so results are deterministic for a given (M, N, K) but the fp32
  * summation order of those tiles differs from the unsplit kernel (same bf16 rounding points). Such launches are
@@ -211,6 +212,10 @@ MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L,
 
 /* Debug/testing: copy of the residual stream after `layer` layers is kept when enabled (device pointer returned). */
 MMDP_API const uint16_t* mmdp_model_hidden(mmdp_model* m);
+/* Sticky device-side error flags of the forwards issued so far, read and cleared (this call SYNCHRONISES `stream`):
+ * bit 0 = a token id was outside [0, vocab_size) (torch raises IndexError in nn.Embedding; the kernel read row 0),
+ * bit 1 = a logits row index (rows_a / rows_b) was outside [0, B*L). The host mirrors call it at their read-back point. */
+MMDP_API int mmdp_model_error_flags(mmdp_model* m, int32_t* flags_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,7 @@ SIGNATURES = {
     "mmdp_model_set_rope": (_i, [_vp, _vp, _vp, _i, _vp]),
     "mmdp_model_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "mmdp_model_hidden": (_vp, [_vp]),
+    "mmdp_model_error_flags": (_i, [_vp, C.POINTER(C.c_int32), _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -57,7 +57,8 @@ struct mmdp_model {
     // workspace
     int Mmax = 0, Lpad_max = 0;
     bf16 *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *vt = nullptr, *att = nullptr, *h = nullptr, *xr = nullptr;
-    int vt_B = 0, vt_Lpad = 0;  // layout the vt buffer was last zeroed for
+    int* err_flag = nullptr;  // device: bit 0 = token id out of range, bit 1 = logits row index out of range
+    int vt_B = 0, vt_Lpad = 0, vt_L = 0;  // layout / length the vt buffer was last zeroed for
     std::vector<void*> allocs;
 };
 
@@ -151,7 +152,7 @@ MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches) { 
 MMDP_API long long mmdp_launch_count(int reset) { return launch_count(reset); }
 MMDP_API void mmdp_set_gemm_pair(int on) { set_gemm_pair_mode(on); }
 MMDP_API void mmdp_set_attention_version(int v) { set_attention_version(v); }
-MMDP_API void mmdp_set_gemm_splitk(int mode) { set_gemm_splitk_mode(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
+MMDP_API void mmdp_set_gemm_splitk(int mode) { set_gemm_splitk_mode(mode < 0 ? 0 : (mode > 3 ? 3 : mode)); }
 MMDP_API void mmdp_set_pdl(int on) { set_pdl_mode(on); }
 MMDP_API int mmdp_set_option(const char* key, int value) { return key ? set_opt(key, value) : set_error("mmdp_set_option: null key"); }
 
@@ -197,6 +198,8 @@ MMDP_API int mmdp_model_create(const mmdp_model_config* c, mmdp_model** out) {
     rc |= dev_alloc(m, (void**)&m->vt, (size_t)c->max_batch * d * m->Lpad_max * 2);
     rc |= dev_alloc(m, (void**)&m->cos_tab, (size_t)c->max_seq_len * 64 * 4);
     rc |= dev_alloc(m, (void**)&m->sin_tab, (size_t)c->max_seq_len * 64 * 4);
+    rc |= dev_alloc(m, (void**)&m->err_flag, sizeof(int));
+    if (!rc && cudaMemset(m->err_flag, 0, sizeof(int)) != cudaSuccess) rc = set_error("mmdp_model_create: cudaMemset failed");
     if (rc) {
         mmdp_model_destroy(m);
         return -1;
@@ -267,6 +270,17 @@ MMDP_API int mmdp_model_set_rope(mmdp_model* m, const float* cos_tab, const floa
 
 MMDP_API const uint16_t* mmdp_model_hidden(mmdp_model* m) { return m ? (const uint16_t*)m->x : nullptr; }
 
+MMDP_API int mmdp_model_error_flags(mmdp_model* m, int32_t* flags_host, void* stream) {
+    if (!m || !flags_host) return set_error("mmdp_model_error_flags: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int v = 0;
+    MMDP_CUDA(cudaMemcpyAsync(&v, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MMDP_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), s));
+    MMDP_CUDA(cudaStreamSynchronize(s));
+    *flags_host = v;
+    return 0;
+}
+
 MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16_t* full_logits, const int32_t* rows_a,
                        int n_a, uint16_t* out_a, const int32_t* rows_b, int n_b, int col0_b, int ncols_b,
                        uint16_t* out_b, void* stream) {
@@ -281,14 +295,16 @@ MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L,
     const int d = c.d_model, ff = c.mlp_hidden, V = c.vocab_size, H = c.n_heads;
     const int M = B * L;
     const int Lpad = ((L + 7) / 8) * 8;
-    if (m->vt_Lpad != Lpad) {  // (indexing depends on Lpad only; batch rows are disjoint)
-        // pad columns of V^T must be zero (they meet P == 0 in the P·V MMA); re-zero when the layout changes
+    if (m->vt_Lpad != Lpad || L < m->vt_L) {  // (indexing depends on Lpad only; batch rows are disjoint)
+        // pad columns [L, Lpad) of V^T must be zero (they meet P == 0 in the P·V MMA): re-zero when the layout changes or
+        // when L shrinks inside the same Lpad (columns a longer forward wrote would otherwise stay behind)
         MMDP_CUDA(cudaMemsetAsync(m->vt, 0, (size_t)c.max_batch * d * m->Lpad_max * 2, s));
         m->vt_B = B;
         m->vt_Lpad = Lpad;
     }
+    m->vt_L = L;
     const float scale = 1.0f / sqrtf(128.0f);
-    if (embed_rows(ids, m->wte, m->x, M, d, V, s)) return -1;
+    if (embed_rows(ids, m->wte, m->x, M, d, V, s, m->err_flag)) return -1;
     QkvRopeArgs qa{m->q, m->k, m->vt, m->cos_tab, m->sin_tab, L, Lpad, d, H};
     for (int li = 0; li < c.n_layers; ++li) {
         const LayerWeights& l = m->layers[li];
@@ -307,14 +323,14 @@ MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L,
     if (n_a > 0) {
         if (!rows_a || !out_a) return set_error("mmdp_model_forward: rows_a/out_a null");
         if (n_a > m->Mmax) return set_error("mmdp_model_forward: too many rows_a");
-        if (rmsnorm_rows(m->x, d, rows_a, m->ln_f, m->xr, d, n_a, d, c.rms_eps, s)) return -1;
+        if (rmsnorm_rows(m->x, d, rows_a, m->ln_f, m->xr, d, n_a, d, c.rms_eps, s, M, m->err_flag)) return -1;
         if (gemm_bf16(EPI_PLAIN, m->xr, d, m->head, d, n_a, V, d, (bf16*)out_a, V, nullptr, 0, nullptr, s)) return -1;
     }
     if (n_b > 0) {
         if (!rows_b || !out_b) return set_error("mmdp_model_forward: rows_b/out_b null");
         if (n_a + n_b > m->Mmax) return set_error("mmdp_model_forward: too many rows_a + rows_b");
         bf16* xr_b = m->xr + (size_t)n_a * d;
-        if (rmsnorm_rows(m->x, d, rows_b, m->ln_f, xr_b, d, n_b, d, c.rms_eps, s)) return -1;
+        if (rmsnorm_rows(m->x, d, rows_b, m->ln_f, xr_b, d, n_b, d, c.rms_eps, s, M, m->err_flag)) return -1;
         if (gemm_bf16(EPI_PLAIN, xr_b, d, m->head + (size_t)col0_b * d, d, n_b, ncols_b, d, (bf16*)out_b, ncols_b, nullptr, 0, nullptr, s)) return -1;
     }
     return 0;

@@ -9,33 +9,43 @@
 namespace mmdp {
 
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ wte,
-                             __nv_bfloat16* __restrict__ x, int d, int64_t vocab) {
+                             __nv_bfloat16* __restrict__ x, int d, int64_t vocab, int* __restrict__ err) {
     const int row = blockIdx.x;
     pdl_launch_dependents();
     pdl_wait();
     int64_t id = ids[row];
-    if (id < 0 || id >= vocab) id = 0;  // torch would raise; ids are validated on the host, this only avoids OOB reads
+    if (id < 0 || id >= vocab) {
+        // torch raises IndexError here; the kernel reads row 0 instead and raises the context's sticky error flag, which
+        // the host turns into the same exception at its next read-back (mmdp_model_error_flags)
+        if (err && threadIdx.x == 0) atomicOr(err, 1);
+        id = 0;
+    }
     const uint4* src = reinterpret_cast<const uint4*>(wte + (size_t)id * d);
     uint4* dst = reinterpret_cast<uint4*>(x + (size_t)row * d);
     for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
 }
 
 int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, int M, int d, int64_t vocab,
-               cudaStream_t stream) {
+               cudaStream_t stream, int* err) {
     if (d % 8) return set_error("embed: d must be a multiple of 8");
     LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read row + write row
-    MMDP_CUDA(launch_ex(embed_kernel, dim3(M), dim3(128), 0, stream, pdl_mode() != 0, false, ids, wte, x, d, vocab));
+    MMDP_CUDA(launch_ex(embed_kernel, dim3(M), dim3(128), 0, stream, pdl_mode() != 0, false, ids, wte, x, d, vocab, err));
     return 0;
 }
 
 // One CTA per output row. rows == nullptr: input row = output row; else input row = rows[i] (gather).
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
-               const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int d, float eps) {
+               const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int d, float eps, int src_rows,
+               int* __restrict__ err) {
     const int orow = blockIdx.x;
     pdl_launch_dependents();
     pdl_wait();
-    const int irow = rows ? rows[orow] : orow;
+    int irow = rows ? rows[orow] : orow;
+    if (rows && (irow < 0 || irow >= src_rows)) {  // gather index outside the source matrix: flag it, read row 0
+        if (err && threadIdx.x == 0) atomicOr(err, 2);
+        irow = 0;
+    }
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)irow * ldx);
     const uint4* w4 = reinterpret_cast<const uint4*>(w);
     uint4* dst = reinterpret_cast<uint4*>(y + (size_t)orow * ldy);
@@ -115,13 +125,18 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restri
 template <int NV>
 __global__ void __launch_bounds__(256, 2)
 rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
-                    const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int M, float eps) {
+                    const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int M, float eps, int src_rows,
+                    int* __restrict__ err) {
     const int orow = blockIdx.x * 8 + (threadIdx.x >> 5);
     pdl_launch_dependents();
     pdl_wait();
     if (orow >= M) return;
     const int lane = threadIdx.x & 31;
-    const int irow = rows ? rows[orow] : orow;
+    int irow = rows ? rows[orow] : orow;
+    if (rows && (irow < 0 || irow >= src_rows)) {  // gather index outside the source matrix: flag it, read row 0
+        if (err && lane == 0) atomicOr(err, 2);
+        irow = 0;
+    }
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)irow * ldx);
     const uint4* w4 = reinterpret_cast<const uint4*>(w);
     uint4* dst = reinterpret_cast<uint4*>(y + (size_t)orow * ldy);
@@ -178,7 +193,7 @@ rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __r
 }
 
 int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
-                 int M, int d, float eps, cudaStream_t stream) {
+                 int M, int d, float eps, cudaStream_t stream, int src_rows, int* err) {
     if (M <= 0) return 0;
     if ((d % 8) || (ldx % 8) || (ldy % 8)) return set_error("rmsnorm: d/ldx/ldy must be multiples of 8");
     LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read x + write y
@@ -187,12 +202,12 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
     const bool pdl = pdl_mode() != 0;
     cudaError_t e;
     switch (use_warp ? d : -1) {  // warp-per-row variants for the model widths in use; anything else takes the CTA-per-row kernel
-        case 4096: e = launch_ex(rmsnorm_warp_kernel<16>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
-        case 2048: e = launch_ex(rmsnorm_warp_kernel<8>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
-        case 1024: e = launch_ex(rmsnorm_warp_kernel<4>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
-        case 512: e = launch_ex(rmsnorm_warp_kernel<2>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
-        case 256: e = launch_ex(rmsnorm_warp_kernel<1>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps); break;
-        default: e = launch_ex(rmsnorm_kernel, dim3(M), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, d, eps);
+        case 4096: e = launch_ex(rmsnorm_warp_kernel<16>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err); break;
+        case 2048: e = launch_ex(rmsnorm_warp_kernel<8>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err); break;
+        case 1024: e = launch_ex(rmsnorm_warp_kernel<4>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err); break;
+        case 512: e = launch_ex(rmsnorm_warp_kernel<2>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err); break;
+        case 256: e = launch_ex(rmsnorm_warp_kernel<1>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err); break;
+        default: e = launch_ex(rmsnorm_kernel, dim3(M), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, d, eps, src_rows, err);
     }
     MMDP_CUDA(e);
     MMDP_CUDA(cudaGetLastError());
@@ -230,7 +245,7 @@ int resid_add_f32(__nv_bfloat16* x, int ldx, const float* partial, int ldp, int 
 
 int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy, int M, int d, float eps,
             cudaStream_t stream) {
-    return rmsnorm_rows(x, ldx, nullptr, w, y, ldy, M, d, eps, stream);
+    return rmsnorm_rows(x, ldx, nullptr, w, y, ldy, M, d, eps, stream, M, nullptr);
 }
 
 }  // namespace mmdp

@@ -248,7 +248,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // split tail costs 1/splits of a wave plus the partial-sum exchange. Split-K changes the fp32 summation ORDER of the
 // affected tiles (not the rounding points); which tiles are affected depends on (M, N, K) only, so results are
 // deterministic for a given problem shape. MMDP_GEMM_SPLITK: 0 = never, 1 = residual GEMMs only (round-1 behaviour),
-// 2 (default) = every epilogue.
+// 2 (default) = every epilogue where the cost model says it pays, 3 = every epilogue whenever a tail exists (tests).
 struct GemmPlan { int bn, grid, tail, splits, kb_per; };
 int gemm_splitk_mode() { return opt(OPT_GEMM_SPLITK); }
 void set_gemm_splitk_mode(int m) { set_opt("gemm_splitk", m); }
@@ -278,7 +278,7 @@ static GemmPlan plan_gemm(int epi, int M, int N, int K) {
                 splits = (num_k + kb_per - 1) / kb_per;
                 // exchange cost in units of one tile's main loop: publish + finish move 2 x 128 KB per unit through L2
                 // (~4 us) against num_k x ~0.3 us of MMA time
-                const double exch = 12.0 / num_k + 0.04;
+                const double exch = mode >= 3 ? 0.0 : 12.0 / num_k + 0.04;  // mode 3 (tests): split whenever structurally possible
                 const double split_waves = (double)(full / g) + (double)kb_per / num_k + exch;
                 if (split_waves < waves) {
                     pl.tail = tail; pl.splits = splits; pl.kb_per = kb_per;

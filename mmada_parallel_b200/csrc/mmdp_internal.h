@@ -120,13 +120,15 @@ void set_attention_version(int v);
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                   int H, int L, int Lpad, float scale, cudaStream_t stream);
 
+// err (nullable): device int, bit 0 is raised when an id is outside [0, vocab) (the kernel then reads row 0)
 int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, int M, int d, int64_t vocab,
-               cudaStream_t stream);
+               cudaStream_t stream, int* err = nullptr);
 int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy, int M, int d, float eps,
             cudaStream_t stream);
 int resid_add_f32(__nv_bfloat16* x, int ldx, const float* partial, int ldp, int M, int d, cudaStream_t stream);
+// src_rows / err: gather indices outside [0, src_rows) raise bit 1 of *err (nullable) and read row 0
 int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
-                 int M, int d, float eps, cudaStream_t stream);
+                 int M, int d, float eps, cudaStream_t stream, int src_rows = 0x7fffffff, int* err = nullptr);
 
 int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int R, int V, float text_cfg,
               const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,

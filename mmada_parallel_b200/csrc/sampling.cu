@@ -126,22 +126,18 @@ __global__ void __launch_bounds__(kThreads) text_rows_kernel(TextRowArgs a) {
 }
 
 // text step, kernel 2: confidence top-k (k largest, ties -> lower index) and commit into the id buffer
-__global__ void text_commit_kernel(const int64_t* __restrict__ x0, const double* __restrict__ conf, int64_t* ids, int R,
-                                   int64_t mask_id, int k) {
-    extern __shared__ double s_conf[];
-    const int i = threadIdx.x;
-    bool masked = false;
-    double c = -INFINITY;
-    if (i < R) {
-        masked = ids[i] == mask_id;
-        c = masked ? conf[i] : -INFINITY;
-        s_conf[i] = c;
-    }
+static constexpr int kTextMaxR = 4096;
+__global__ void __launch_bounds__(1024) text_commit_kernel(const int64_t* __restrict__ x0, const double* __restrict__ conf, int64_t* ids, int R,
+                                                           int64_t mask_id, int k) {
+    extern __shared__ double s_confd[];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) s_confd[i] = (ids[i] == mask_id) ? conf[i] : -INFINITY;
     __syncthreads();
-    if (i < R) {
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        const bool masked = ids[i] == mask_id;  // (only this thread writes ids[i])
+        const double c = s_confd[i];
         int rank = 0;
         for (int j = 0; j < R; ++j) {
-            const double cj = s_conf[j];
+            const double cj = s_confd[j];
             rank += (cj > c) || (cj == c && j < i);
         }
         if (rank < k && masked) ids[i] = x0[i];
@@ -152,7 +148,7 @@ int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld
               const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
               int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream) {
     if (R <= 0) return 0;
-    if (R > 1024) return set_error("text_step: at most 1024 text positions");
+    if (R > kTextMaxR) return set_error("text_step: at most %d text positions", kTextMaxR);
     if ((V % 8) || (ld % 8) || (unoise && (ld_noise % 8))) return set_error("text_step: V/ld must be multiples of 8");
     TextRowArgs a{cond, uncond, unoise, ld, ld_noise, V, text_cfg, temperature, x0_ws, conf_ws};
     {
@@ -160,7 +156,7 @@ int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld
         text_rows_kernel<512><<<R, 512, 0, stream>>>(a);
     }
     MMDP_CUDA(cudaGetLastError());
-    const int threads = ((R + 31) / 32) * 32;
+    const int threads = R >= 1024 ? 1024 : ((R + 31) / 32) * 32;
     LaunchScope ls2(LK_SAMPLE, (double)R * 24, stream);
     text_commit_kernel<<<1, threads, R * sizeof(double), stream>>>(x0_ws, conf_ws, ids_text, R, mask_id, k);
     MMDP_CUDA(cudaGetLastError());
@@ -316,7 +312,7 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
 // image step, kernel 2 (single CTA): confidence jitter -> stable rank -> re-mask -> write ids
 // ------------------------------------------------------------------------------------------------
 struct RemaskArgs {
-    int N;                 // number of VQ tokens (<= 1024)
+    int N;                 // number of VQ tokens (<= kRemaskMaxN)
     int variant;           // 0 = A, 1 = M
     const int32_t* sampled;
     const float* selp;
@@ -333,26 +329,29 @@ struct RemaskArgs {
 
 __device__ __forceinline__ float log_bf16(float x) { return bf16_round(logf(x)); }
 
+static constexpr int kRemaskMaxN = 4096;  // 768x768 images of the reference app are 2304 VQ tokens
+static constexpr int kRemaskPer = kRemaskMaxN / 1024;
+
 __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
-    __shared__ float s_conf[1024];
+    extern __shared__ float s_conf[];  // [N]
     __shared__ int s_cnt[32];
     __shared__ float s_cut;
-    const int i = threadIdx.x;
-    const bool in = i < a.N;
-    const int unk = in ? a.unknown[i] : 0;
-    int cnt = unk;
+    const int tid = threadIdx.x;
+    int cnt = 0;
+    float conf[kRemaskPer];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((i & 31) == 0) s_cnt[i >> 5] = cnt;
-    float conf = INFINITY;
-    if (in) {
+    for (int t = 0; t < kRemaskPer; ++t) {
+        const int i = tid + t * 1024;
+        conf[t] = INFINITY;
+        if (i >= a.N) continue;
+        cnt += a.unknown[i] ? 1 : 0;
         const float p = a.selp[i];
         const float nz = a.noise ? __bfloat162float(a.noise[i]) : 0.f;
         if (a.variant == 0) {
             // confidence = log(probs + 1e-10) + temperature * noise     (parallel_generator.py:36)
             const float lp = log_bf16(bf16_round(__fadd_rn(p, 1e-10f)));
             const float tn = a.noise ? bf16_round(__fmul_rn(nz, a.temp)) : 0.f;
-            conf = bf16_round(__fadd_rn(lp, tn));
+            conf[t] = bf16_round(__fadd_rn(lp, tn));
         } else {
             // confidence = log(clamp(p,1e-20)) + temperature * (-log(clamp(-log(clamp(u,1e-20)),1e-20)))  (sampling.py:9-16,31-32)
             const float lp = log_bf16(fmaxf(p, bf16_round(1e-20f)));
@@ -364,10 +363,13 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
                 g = -g;
             }
             const float tn = bf16_round(__fmul_rn(g, a.temp));
-            conf = bf16_round(__fadd_rn(lp, tn));
+            conf[t] = bf16_round(__fadd_rn(lp, tn));
         }
+        s_conf[i] = conf[t];
     }
-    s_conf[i] = conf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
     __syncthreads();
     int unknown_cnt = 0;
     for (int j = 0; j < 32; ++j) unknown_cnt += s_cnt[j];
@@ -375,36 +377,41 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
     int k = a.sched_len < unknown_cnt - 1 ? a.sched_len : unknown_cnt - 1;
     if (k < 1) k = 1;
     if (a.variant == 0) { if (k > a.N - 1) k = a.N - 1; if (k < 0) k = 0; }  // mask_by_random_topk clamps to [0, N-1]
-    int rank = 0;
-    if (in) {
+    int rank[kRemaskPer];
+#pragma unroll
+    for (int t = 0; t < kRemaskPer; ++t) {
+        const int i = tid + t * 1024;
+        rank[t] = 0;
+        if (i >= a.N) continue;
+        const float c = conf[t];
+        int r = 0;
         for (int j = 0; j < a.N; ++j) {
             const float cj = s_conf[j];
-            rank += (cj < conf) || (cj == conf && j < i);  // stable ascending sort position
+            r += (cj < c) || (cj == c && j < i);  // stable ascending sort position
         }
+        rank[t] = r;
+        if (a.variant != 0 && r == (k < a.N ? k : a.N - 1)) s_cut = c;  // sorted_confidence[mask_len]
     }
-    bool masking = false;
-    if (a.variant == 0) {
-        masking = in && rank < k;
-    } else {
-        if (in && rank == (k < a.N ? k : a.N - 1)) s_cut = conf;  // sorted_confidence[mask_len]
-        __syncthreads();
-        masking = in && conf < s_cut;
-    }
-    if (in) {
+    if (a.variant != 0) __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kRemaskPer; ++t) {
+        const int i = tid + t * 1024;
+        if (i >= a.N) continue;
+        const bool masking = a.variant == 0 ? rank[t] < k : conf[t] < s_cut;
         a.ids[a.pos[i]] = masking ? a.mask_id : (int64_t)a.sampled[i] + a.vq_offset;
         if (a.masking_out) a.masking_out[i] = masking ? 1 : 0;
     }
-    if (i == 0 && a.mask_len_out) *a.mask_len_out = k;
+    if (tid == 0 && a.mask_len_out) *a.mask_len_out = k;
 }
 
 int image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
                  const __nv_bfloat16* conf_noise, float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id,
                  int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream) {
-    if (N <= 0 || N > 1024) return set_error("image_remask: N must be in [1, 1024]");
+    if (N <= 0 || N > kRemaskMaxN) return set_error("image_remask: N must be in [1, %d]", kRemaskMaxN);
     RemaskArgs ma{N, variant, sampled, selp, unknown, conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
                   mask_len_out, masking_out};
     LaunchScope ls(LK_SAMPLE, (double)N * 24, stream);
-    image_remask_kernel<<<1, 1024, 0, stream>>>(ma);
+    image_remask_kernel<<<1, 1024, N * sizeof(float), stream>>>(ma);
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -414,7 +421,7 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
                float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset,
                int32_t* sampled_ws, float* selp_ws, uint8_t* unknown_ws, __nv_bfloat16* probs_out,
                int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream) {
-    if (N <= 0 || N > 1024) return set_error("image_step: N must be in [1, 1024]");
+    if (N <= 0 || N > kRemaskMaxN) return set_error("image_step: N must be in [1, %d]", kRemaskMaxN);
     if (C <= 0 || (C % 8) || C > kImgThreads * kImgMaxPer * 8) return set_error("image_step: codebook size must be a multiple of 8 and <= 8192");
     if (ld % 8) return set_error("image_step: ld must be a multiple of 8");
     if (variant == 1 && !unc_a) return set_error("image_step: variant M needs uncond logits");

@@ -26,6 +26,8 @@ from ..schedule import (cosine_schedule, get_num_transfer_tokens as _num_transfe
 
 MASK_TOKEN = 126336
 NEW_LINE = 126084
+# limits of the single-CTA re-mask / commit kernels and of the per-row image kernel (csrc/sampling.cu)
+MAX_VQ_TOKENS, MAX_TEXT_TOKENS, MAX_CODEBOOK = 4096, 4096, 8192
 
 __all__ = ["generate_ti2ti", "cosine_schedule", "get_num_transfer_tokens", "add_gumbel_noise", "mask_by_random_topk"]
 
@@ -75,6 +77,12 @@ class DenoiseState:
         device = model.device
         self.model = model
         self.L = ids_host.shape[1]
+        # limits of the sampling kernels (csrc/sampling.cu), checked before any forward runs
+        if seq_len > MAX_VQ_TOKENS or text_end - text_start > MAX_TEXT_TOKENS:
+            raise ValueError(f"at most {MAX_VQ_TOKENS} VQ tokens and {MAX_TEXT_TOKENS} text positions are supported "
+                             f"(got {seq_len} / {text_end - text_start})")
+        if codebook_size > MAX_CODEBOOK or codebook_size % 8:
+            raise ValueError(f"codebook_size must be a multiple of 8 and <= {MAX_CODEBOOK} (got {codebook_size})")
         total_image_len = seq_len + seq_len // newline_every
         image_end = image_start + total_image_len
         self.text_start, self.text_end, self.seq_len = text_start, text_end, seq_len
@@ -112,18 +120,22 @@ class DenoiseState:
 
 def denoise_step(st: DenoiseState, step: int, is_img: bool, k_transfer: int, noise: "_Noise", text_steps: int,
                  temperature: float, text_temperature: float, cfg_scale: float, cfg_img: float, noise_schedule,
-                 text_vocab_size: int, codebook_size: int, _trace: Optional[list] = None) -> None:
+                 text_vocab_size: int, codebook_size: int, _trace: Optional[list] = None, text_masks_left: int = 1) -> None:
     """One iteration of the step loop (parallel_generator.py:177-344; the preview loop app.py:177-305 runs the same body)
-    on device-resident state. No host<->device synchronisation happens in here."""
+    on device-resident state. No host<->device synchronisation happens in here.
+    `text_masks_left` is the number of masked text positions entering this step (known on the host without a read-back:
+    total - sum of the transfer counts so far); at 0 the reference skips the whole text step INCLUDING its Gumbel draw
+    (`if text_masked_indices.sum() > 0`, :183), so no generator state is consumed here either."""
     model, ids, V, n_text, seq_len = st.model, st.ids, st.model.vocab_rows, st.n_text, st.seq_len
     # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
     model.forward_rows(ids, rows_a=st.text_rows, out_a=st.text_logits, rows_b=st.pos if is_img else None,
                        col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.cond_vq if is_img else None)
-    # ---- text step (:181-217). A fully un-masked span makes the kernel a no-op, like the `.sum() > 0` guard.
-    un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
-    check(lib.mmdp_text_step(ptr(st.text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
-                             ids.data_ptr() + st.text_start * 8, MASK_TOKEN, int(k_transfer), ptr(st.x0_ws), ptr(st.conf_ws),
-                             stream_ptr()))
+    # ---- text step (:181-217), guarded like the reference's `.sum() > 0` (:183)
+    if text_masks_left > 0:
+        un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
+        check(lib.mmdp_text_step(ptr(st.text_logits), None, V, n_text, V, 0.0, ptr(un), V, float(text_temperature),
+                                 ids.data_ptr() + st.text_start * 8, MASK_TOKEN, int(k_transfer), ptr(st.x0_ws), ptr(st.conf_ws),
+                                 stream_ptr()))
     if _trace is not None:
         _trace.append({"step": step, "ids_after_text": ids[0].clone()})
     if not is_img:
@@ -168,9 +180,11 @@ def denoise_loop(st: DenoiseState, text_steps: int, timesteps: int, temperature:
     num_transfer = _num_transfer_row(st.total_masks, text_steps)                              # :153-154
     img_steps = set(image_generation_step_indices(text_steps, timesteps))                     # :157-159
     noise = _Noise(generator, st.model.device)
+    masks_left = st.total_masks
     for step in range(text_steps):
         denoise_step(st, step, step in img_steps, num_transfer[step], noise, text_steps, temperature, text_temperature,
-                     cfg_scale, cfg_img, noise_schedule, text_vocab_size, codebook_size, _trace)
+                     cfg_scale, cfg_img, noise_schedule, text_vocab_size, codebook_size, _trace, text_masks_left=masks_left)
+        masks_left -= num_transfer[step]
     return st.ids
 
 
@@ -223,6 +237,8 @@ def generate_ti2ti(
 
     # ---- extract results (:346-368): the only device->host read of the call
     final = ids[0].cpu()
+    if hasattr(model, "raise_device_errors"):
+        model.raise_device_errors()   # e.g. a token id outside the vocabulary: IndexError, like nn.Embedding in the reference
     text_tokens = [t for t in final[text_start:text_end].tolist() if t != MASK_TOKEN]
     generated_text = tokenizer.decode(text_tokens, skip_special_tokens=True) if tokenizer is not None else text_tokens
     image_tokens: List[int] = []

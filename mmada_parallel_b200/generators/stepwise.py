@@ -78,11 +78,13 @@ def generate_ti2ti_stepwise(
         return img
 
     last_image = None
+    masks_left = st.total_masks
     yield 0, decode_text_with_masks(ids, text_start, text_end, tokenizer, MASK_TOKEN), None, f"Step 0/{text_steps}"
     for step in range(text_steps):
         is_img = step in img_steps
         denoise_step(st, step, is_img, num_transfer[step], noise, text_steps, temperature, text_temperature, cfg_scale,
-                     cfg_img, noise_schedule, text_vocab_size, codebook_size, _trace)
+                     cfg_img, noise_schedule, text_vocab_size, codebook_size, _trace, text_masks_left=masks_left)
+        masks_left -= num_transfer[step]
         emit = step % 5 == 0 or is_img or step == text_steps - 1                                 # :345
         if not (emit or is_img):
             continue

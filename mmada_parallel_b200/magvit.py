@@ -61,6 +61,43 @@ class VQGANDecoder:
             raise KeyError(f"VQGANDecoder.load_state_dict: {missing} missing ({buf.value.decode()[:200]}), unexpected={unexpected[:6]}")
         return SimpleNamespace(missing_keys=buf.value.decode().split(), unexpected_keys=unexpected)
 
+    def parameter_shapes(self) -> Dict[str, tuple]:
+        """Names and shapes of the parameters this decoder expects (the reference module's registration names, prefix
+        'decoder.'): lets callers build or validate a state dict without instantiating the reference nn.Module."""
+        c = self.cfg
+        sh: Dict[str, tuple] = {}
+
+        def add(name, *shape):
+            sh[name + ".weight"] = shape
+            sh[name + ".bias"] = (shape[0],)
+
+        def res(name, cin, cout):
+            add(name + ".norm1", cin)
+            add(name + ".conv1", cout, cin, 3, 3)
+            add(name + ".norm2", cout)
+            add(name + ".conv2", cout, cout, 3, 3)
+            if cin != cout:
+                add(name + ".nin_shortcut", cout, cin, 1, 1)
+
+        width = c.ch * c.ch_mult[-1]
+        add("decoder.conv_in", width, c.z_channels, 3, 3)
+        res("decoder.mid.block_1", width, width)
+        add("decoder.mid.attn_1.norm", width)
+        for n in ("q", "k", "v", "proj_out"):
+            add("decoder.mid.attn_1." + n, width, width, 1, 1)
+        res("decoder.mid.block_2", width, width)
+        for lvl in range(len(c.ch_mult) - 1, -1, -1):
+            out_w = c.ch * c.ch_mult[lvl]
+            for blk in range(c.num_res_blocks[lvl]):
+                res(f"decoder.up.{lvl}.block.{blk}", width, out_w)
+                width = out_w
+            if lvl:
+                add(f"decoder.up.{lvl}.upsample.conv", width, width, 3, 3)
+        add("decoder.norm_out", width)
+        add("decoder.conv_out", c.out_ch, width, 3, 3)
+        add("decoder.post_quant_conv", c.z_channels, c.z_channels, 1, 1)
+        return sh
+
     def decode_ids(self, ids: torch.Tensor, shape=None) -> torch.Tensor:
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
         b, n = ids.shape

@@ -68,6 +68,13 @@ class LLaDAForMultiModalGeneration:
                 raise NotImplementedError(f"config.{flag}=True is not supported by the B200 hot path")
         if not g("rope", True) or not g("rope_full_precision", True):
             raise NotImplementedError("the hot path implements full-precision RoPE only")
+        # the kernels implement LLaDALlamaBlock + SwiGLU(silu) + RMSLayerNorm only (modeling_llada.py:906-972, :315-329);
+        # a config that asks for another block / activation / norm must not be computed as if it were this one
+        for key, ok in (("block_type", ("llama",)), ("activation_type", ("silu", "swiglu")), ("layer_norm_type", ("rms",))):
+            v = g(key, None)
+            v = getattr(v, "value", v)  # the reference uses StrEnum members
+            if v is not None and str(v).lower() not in ok:
+                raise NotImplementedError(f"config.{key}={v!r} is not supported by the B200 hot path (needs one of {ok})")
         cfg = _lib.ModelConfig(self.d_model, self.n_heads, self.n_layers, self.mlp_hidden, self.vocab_rows,
                                self.max_seq_len, self.max_batch, self.rms_eps)
         handle = C.c_void_p()
@@ -159,6 +166,16 @@ class LLaDAForMultiModalGeneration:
 
     def to(self, *_a, **_k):
         return self
+
+    def raise_device_errors(self) -> None:
+        """Reads and clears the sticky device-side error flags of the forwards issued so far (synchronises the stream).
+        The kernels never read out of bounds; they flag what torch would have raised for."""
+        flags = C.c_int32(0)
+        check(lib.mmdp_model_error_flags(self._h, C.byref(flags), stream_ptr()))
+        if flags.value & 1:
+            raise IndexError("index out of range in self (a token id is outside [0, vocab_size))")
+        if flags.value & 2:
+            raise IndexError("a logits row index is outside [0, batch * seq_len)")
 
     # ------------------------------------------------------------------------------------------------------------
     # forward

@@ -197,6 +197,135 @@ def test_full_size_properties():
     assert torch.isfinite(a2.float()).all() and a2.float().abs().max() > 0.1
 
 
+def _device_view_bf16(ptr_value, numel):
+    """A torch view of `numel` bf16 elements at a raw device address (the context's workspace), via __cuda_array_interface__."""
+    class _Raw:
+        pass
+    r = _Raw()
+    r.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<u2", "data": (int(ptr_value), False), "version": 3}
+    return torch.as_tensor(r, device="cuda").view(torch.bfloat16)
+
+
+def test_full_size_block_and_head_vs_oracle():
+    """BASELINE shapes against the ORACLE (not against itself): one LLaDA block at d=4096 / ff=12288 / 32 heads / L=2414 plus
+    the restricted LM head (256 text rows x 134 656 columns, 1024 image rows x the 8192-column codebook window), B200 vs
+    oracle.llada on the box's CPU with the same bf16 weights. This is the production tile schedule: 19 m-tiles, the split-K
+    tails of the GEMMs, 608 attention CTAs with the KV-split partial wave. Bound: 4 bf16 ulp of the tensor's scale (same as
+    the tiny-model logit test), and the mean error far below one ulp."""
+    import time
+    from mmada_parallel_b200 import _lib
+    from mmada_parallel_b200.model import LLaDAForMultiModalGeneration
+    from oracle import llada
+    cfg = llada.make_config(d_model=4096, n_heads=32, n_layers=1, mlp_hidden_size=12288, vocab_size=134656, max_sequence_length=2432)
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    d, ff, V, L = 4096, 12288, 134656, 2414
+
+    def rnd(*s, std):
+        return (torch.randn(*s, device="cuda", generator=g) * std).to(torch.bfloat16)
+
+    p = "model.transformer.blocks.0."
+    sd = {"model.transformer.wte.weight": rnd(V, d, std=0.02), "model.transformer.ff_out.weight": rnd(V, d, std=d ** -0.5),
+          "model.transformer.ln_f.weight": (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).to(torch.bfloat16)}
+    for n, shape, std in [("q_proj", (d, d), d ** -0.5), ("k_proj", (d, d), d ** -0.5), ("v_proj", (d, d), d ** -0.5),
+                          ("attn_out", (d, d), d ** -0.5), ("ff_proj", (ff, d), d ** -0.5), ("up_proj", (ff, d), d ** -0.5),
+                          ("ff_out", (d, ff), ff ** -0.5)]:
+        sd[p + n + ".weight"] = rnd(*shape, std=std)
+    sd[p + "attn_norm.weight"] = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).to(torch.bfloat16)
+    sd[p + "ff_norm.weight"] = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).to(torch.bfloat16)
+    m = LLaDAForMultiModalGeneration(cfg, max_seq_len=2432, max_batch=1)
+    m.load_state_dict(sd)
+    ids = torch.randint(0, 126000, (1, L), device="cuda", generator=g)
+    text_rows = torch.arange(2157, 2413, dtype=torch.int32, device="cuda")
+    img_rows = torch.arange(1100, 1100 + 1024, dtype=torch.int32, device="cuda")
+    a, b = m.forward_rows(ids, rows_a=text_rows, rows_b=img_rows, col0_b=126356, ncols_b=8192)
+    # the residual stream after the block lives in the context's workspace (mmdp_model_hidden)
+    hidden = _device_view_bf16(_lib.lib.mmdp_model_hidden(m._h), L * d).view(L, d).clone()
+    torch.cuda.synchronize()
+
+    # ---- the oracle on the CPU, same weights
+    w = {k: v.cpu() for k, v in sd.items()}
+    t0 = time.time()
+    with torch.no_grad():
+        x = torch.nn.functional.embedding(ids.cpu(), w["model.transformer.wte.weight"])
+        pos_sin, pos_cos = llada.rotary_tables(128, cfg.rope_theta, L)
+        x = llada.block_forward(x, w, p, cfg, pos_sin, pos_cos)
+        xn = llada.rms_norm(x, w["model.transformer.ln_f.weight"], cfg.rms_norm_eps)[0]
+        head = w["model.transformer.ff_out.weight"]
+        a_o = torch.nn.functional.linear(xn[2157:2413], head)
+        b_o = torch.nn.functional.linear(xn[1100:1100 + 1024], head[126356:126356 + 8192])
+    print(f"[full-size oracle] CPU block + heads: {time.time() - t0:.1f} s")
+
+    def check(got, want, what):
+        gq, wq = got.float().cpu(), want.float()
+        scale = wq.abs().max().item()
+        err = (gq - wq).abs()
+        ulp = scale * 2.0 ** -8
+        print(f"[full-size] {what}: scale {scale:.3f}, max err {err.max().item() / ulp:.2f} ulp, mean err {err.mean().item() / ulp:.4f} ulp, "
+              f"bit-equal {float((gq == wq).float().mean()):.4f}")
+        assert torch.isfinite(gq).all(), what
+        assert err.max().item() <= 4 * ulp, (what, err.max().item() / ulp)
+        assert err.mean().item() <= 0.25 * ulp, (what, err.mean().item() / ulp)
+
+    check(hidden, x[0], "residual stream after the block")
+    check(a, a_o, "text-row logits")
+    check(b, b_o, "image-row codebook logits")
+    # greedy decisions: equal wherever the oracle's own top-1/top-2 margin exceeds twice the bound
+    top2 = a_o.float().topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 8 * a_o.float().abs().max() * 2.0 ** -8
+    assert int(clear.sum()) >= 16
+    assert torch.equal(a.float().cpu().argmax(-1)[clear], a_o.float().argmax(-1)[clear])
+
+
+def test_text_masks_fewer_than_steps_lockstep():
+    """Total text masks < text_steps with text_temperature > 0: the last steps enter with zero masked text positions. The
+    reference skips the text step there INCLUDING its Gumbel draw (`if text_masked_indices.sum() > 0`, :183), so the
+    generator must not advance; the final image steps then draw the same multinomial / randn noise as the oracle."""
+    from mmada_parallel_b200.generators.parallel_generator import generate_ti2ti
+    t = load_golden("trajectory_a_tiny.pt")
+    model, cfg, _ = tiny_gpu_model(t["meta"])
+    lay = t["layout"]
+    ids = lay["input_ids"].clone()
+    ts, te = lay["text_start"], lay["text_end"]
+    n_text = te - ts
+    # keep only 5 masks in the text span (prefilled text elsewhere), run 12 steps: the last steps have nothing to un-mask
+    keep = torch.arange(ts, te)[:: max(1, n_text // 5)][:5]
+    filler = torch.randint(1000, 2000, (n_text,), generator=torch.Generator().manual_seed(3))
+    ids[0, ts:te] = filler
+    ids[0, keep] = 126336
+    kw = dict(text_steps=12, timesteps=6, temperature=1.0, text_temperature=0.8, cfg_scale=0.0, cfg_img=3.0)
+    backed = GpuBackedOracleModel(model)
+    args = _args(lay)
+    torch.manual_seed(5)
+    tr_o = []
+    img_o, txt_o = G.generate_ti2ti(backed, ids, generator=torch.Generator().manual_seed(77), trace=tr_o, stable_sort=True, **args, **kw)
+    torch.manual_seed(5)
+    tr_g = []
+    with quiet():
+        img_g, txt_g = generate_ti2ti(model, ids, generator=torch.Generator().manual_seed(77), _trace=tr_g, **args, **kw)
+    assert len(tr_o) == len(tr_g) == 12
+    for so, sg in zip(tr_o, tr_g):
+        assert torch.equal(so["ids_after_text"], sg["ids_after_text"].cpu()), (so["step"], "text")
+        if "ids_after_image" in so:
+            assert torch.equal(so["ids_after_image"], sg["ids_after_image"].cpu()), (so["step"], "image")
+    assert img_g == img_o and txt_g == txt_o
+
+
+def test_device_error_flags_and_limits():
+    """Token ids outside the vocabulary raise IndexError at the read-back point (nn.Embedding raises in the reference); limits of
+    the sampling kernels are checked before any forward runs."""
+    from mmada_parallel_b200.generators.parallel_generator import generate_ti2ti
+    t = load_golden("trajectory_a_tiny.pt")
+    model, cfg, _ = tiny_gpu_model(t["meta"])
+    lay = t["layout"]
+    bad = lay["input_ids"].clone()
+    bad[0, 0] = cfg.vocab_size + 5
+    with pytest.raises(IndexError), quiet():
+        generate_ti2ti(model, bad, text_steps=2, timesteps=1, **_args(lay))
+    model.raise_device_errors()  # the flags were cleared by the read above: no second raise
+    with pytest.raises(ValueError), quiet():
+        generate_ti2ti(model, lay["input_ids"], text_steps=2, timesteps=1, codebook_size=16384, **_args(lay))
+
+
 class _RecordingDecoder:
     """Native-protocol VQ decoder stand-in: records the ids it is asked to decode, returns a black image."""
 

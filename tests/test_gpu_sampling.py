@@ -128,6 +128,24 @@ def _check_against_oracle(out, orc, variant):
     return bool(same.all())
 
 
+def _assert_writeback_exact(variant, out, ids, pos, sched, temp, noise, OFF, N):
+    """UNCONDITIONAL check of the integer stage (confidence -> mask_len -> re-mask -> id write-back): the oracle's
+    mask_by_random_topk is evaluated on the kernel's OWN stage-1 results (sampled id, selected bf16 probability, unknown
+    flag), so there is no floating-point freedom left - mask_len, the mask and every written id must be equal."""
+    unknown = out["unknown"]
+    selected = out["selp"].to(torch.bfloat16)
+    mask_len = max(1, min(int(unknown.sum()) - 1, sched))
+    assert out["mask_len"] == (min(mask_len, N - 1) if variant == "A" else mask_len)
+    if variant == "A":
+        masking, _ = S.mask_by_random_topk_a(mask_len, selected, temp, noise, stable=True)
+    else:
+        masking, _ = S.mask_by_random_topk_m(mask_len, selected, temp, noise)
+    assert torch.equal(out["masking"], masking), "re-mask differs from the oracle on identical stage-1 results"
+    want = ids.clone()
+    want[pos] = torch.where(masking, torch.tensor(MASK), out["sampled"] + OFF)
+    assert torch.equal(out["ids"], want), "id write-back"
+
+
 @pytest.mark.parametrize("seed,s_a,s_b,temp,use_q,sched", [(0, 0.0, 4.0, 0.5, True, 600), (1, 1.5, 4.0, 0.0, False, 3),
                                                           (2, 0.0, 0.0, 1.0, True, 2000), (3, 2.0, 0.0, 0.25, True, -1)])
 def test_image_step_a(seed, s_a, s_b, temp, use_q, sched):
@@ -140,6 +158,7 @@ def test_image_step_a(seed, s_a, s_b, temp, use_q, sched):
     out = run_image_step(0, cond, ua if s_a else None, ub if s_b else None, s_a, s_b, ids, pos, sched, temp,
                          q if use_q else None, rn, OFF)
     assert torch.equal(out["unknown"], orc["unknown"])
+    _assert_writeback_exact("A", out, ids, pos, sched, temp, rn, OFF, N)
     if _check_against_oracle(out, orc, "A"):
         want_ids = ids.clone()
         want_ids[pos] = torch.where(orc["final"] == -1, torch.tensor(MASK), orc["final"] + OFF)
@@ -162,6 +181,7 @@ def test_image_step_m(seed, s, temp, sched):
     orc = S.image_step("M", cond, ua, None, s, 0.0, vqm, MASK, sched, temp, q, un, 8192)
     out = run_image_step(1, cond, ua, None, s, 1 + s, ids, pos, sched, temp, q, un, OFF)
     assert torch.equal(out["unknown"], orc["unknown"])
+    _assert_writeback_exact("M", out, ids, pos, sched, temp, un, OFF, N)
     if _check_against_oracle(out, orc, "M") and torch.equal(out["masking"], orc["masking"]):
         want = ids.clone()
         want[pos] = torch.where(orc["masking"], torch.tensor(MASK), orc["sampled"] + OFF)
@@ -204,3 +224,66 @@ def test_remask_known_answers_from_reference():
                     assert conf[diff].float().unique().numel() == 1, "differs from the reference beyond boundary ties"
                 want_ids = torch.where(stable, torch.tensor(MASK), torch.arange(N) + 1000)
             assert torch.equal(ids.cpu(), want_ids)
+
+
+@pytest.mark.parametrize("variant", ["A", "M"])
+def test_image_step_margin_safe_end_to_end(variant):
+    """Whole image step against the oracle with NO conditional: inputs are built so that no decision sits within
+    floating-point reach of a boundary - every row has one dominant code (logit +12 over unit noise, so its probability is
+    ~1 in bf16 on both sides whatever the last bit of expf), greedy sampling, and temperature 0 with distinct dominant
+    logits per row is replaced by a confidence noise whose magnitude (temp 4 x randn) separates the positions."""
+    g = torch.Generator().manual_seed(123)
+    N, C = 256, 8192
+    cond = torch.randn(N, C, generator=g).to(torch.bfloat16)
+    unc = torch.randn(N, C, generator=g).to(torch.bfloat16)
+    win = torch.randint(0, C, (N,), generator=g)
+    cond[torch.arange(N), win] = 14.0
+    unc[torch.arange(N), win] = 10.0
+    vq = torch.where(torch.rand(N, generator=g) < 0.3, torch.randint(0, C, (N,), generator=g), torch.tensor(-1))
+    noise = (torch.randn(N, generator=g) if variant == "A" else torch.rand(N, generator=g)).to(torch.bfloat16)
+    OFF = 126356 if variant == "A" else 126349
+    pos = torch.arange(N) + 5
+    ids = torch.zeros(N + 10, dtype=torch.int64)
+    ids[pos] = torch.where(vq == -1, torch.tensor(MASK), vq + OFF)
+    sched, temp = 77, 4.0
+    if variant == "A":
+        orc = S.image_step("A", cond, None, unc, 0.0, 2.0, vq, MASK, sched, temp, None, noise, C, stable=True)
+        out = run_image_step(0, cond, None, unc, 0.0, 2.0, ids, pos, sched, temp, None, noise, OFF)
+        final = orc["final"]
+    else:
+        vqm = torch.where(vq == -1, torch.tensor(MASK), vq)
+        orc = S.image_step("M", cond, unc, None, 2.0, 0.0, vqm, MASK, sched, temp, None, noise, C)
+        out = run_image_step(1, cond, unc, None, 2.0, 3.0, ids, pos, sched, temp, None, noise, OFF)
+        final = torch.where(orc["masking"], torch.tensor(-1), orc["sampled"])
+    # the construction must really be margin-safe: distinct confidences around the cut
+    conf = orc["confidence"].float()
+    srt = conf.sort().values
+    assert float((srt[1:] - srt[:-1])[max(0, orc["mask_len"] - 2): orc["mask_len"] + 1].min()) > 0
+    assert torch.equal(out["sampled"], orc["sampled"]) and bool((out["sampled"][orc["unknown"]] == win[orc["unknown"]]).all())
+    assert out["mask_len"] == orc["mask_len"] and torch.equal(out["masking"], orc["masking"])
+    want = ids.clone()
+    want[pos] = torch.where(final == -1, torch.tensor(MASK), final + OFF)
+    assert torch.equal(out["ids"], want)
+
+
+def test_image_and_text_step_large_counts():
+    """768x768 images of the reference app are 2304 VQ tokens; text spans above 1024 positions: the single-CTA re-mask and
+    commit kernels loop over their elements (limits 4096), results equal the oracle's integer logic."""
+    g = torch.Generator().manual_seed(5)
+    N, C, OFF = 2304, 8192, 126356
+    cond = torch.randn(N, C, generator=g).to(torch.bfloat16)
+    win = torch.randint(0, C, (N,), generator=g)
+    cond[torch.arange(N), win] = 14.0
+    vq = torch.where(torch.rand(N, generator=g) < 0.5, torch.randint(0, C, (N,), generator=g), torch.tensor(-1))
+    rn = torch.randn(N, generator=g).to(torch.bfloat16)
+    pos = torch.arange(N) + (torch.arange(N) // 48) + 3
+    ids = torch.zeros(int(pos.max()) + 4, dtype=torch.int64)
+    ids[pos] = torch.where(vq == -1, torch.tensor(MASK), vq + OFF)
+    out = run_image_step(0, cond, None, None, 0.0, 0.0, ids, pos, 700, 3.0, None, rn, OFF)
+    _assert_writeback_exact("A", out, ids, pos, 700, 3.0, rn, OFF, N)
+    R, V = 1500, 4096
+    logits = (torch.randn(R, V, generator=g) * 2).to(torch.bfloat16)
+    tids = torch.where(torch.rand(R, generator=g) < 0.7, torch.tensor(MASK), torch.randint(0, V, (R,), generator=g))
+    new_o, x0_o, conf_o = S.text_step(logits, tids, MASK, 37)
+    new_g, x0_g, conf_g = run_text_step(logits, tids, 37)
+    assert torch.equal(new_g, new_o) and torch.allclose(conf_g, conf_o, rtol=1e-12, atol=0)
