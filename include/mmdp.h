@@ -138,6 +138,26 @@ MMDP_API int mmdp_image_step(int variant, const uint16_t* cond, const uint16_t* 
 /* Second half of the image step on its own (mask_by_random_topk + write-back): parallel_generator.py:23-70, :318-344;
  * M/models/sampling.py:31-36. Inputs are the per-token outputs of the first half (sampled ids, selected probabilities
  * as bf16-representable floats, unknown flags). Ties between equal confidences keep the lower index masked first. */
+/* Text step with variant M's fp64 Gumbel-max (M/models/modeling_mmada.py:49-60 `add_gumbel_noise`, used at :185 and :659 when
+ * the text temperature is > 0): x0 = argmax_v exp(double(l_v)) / (-log u_v)^temperature with u = unoise64 [R, ld_noise] fp64
+ * uniform noise drawn by the caller exactly as the reference draws it (torch.rand_like(logits, dtype=float64), global RNG of
+ * the logits' device). Everything else as mmdp_text_step. */
+MMDP_API int mmdp_text_step_gumbel64(const uint16_t* cond, const uint16_t* uncond, int64_t ld, int R, int V, float text_cfg,
+                            const double* unoise64, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
+                            int k, int64_t* x0_ws, double* conf_ws, void* stream);
+/* One step of A's MaskGit text-to-image decoding, generate_image (MMaDA-Parallel-A/generators/image_generation_generator.py:
+ * 119-208) on the N currently masked positions pos[0..N) of `ids` (compacted by the caller; every ids[pos[i]] == mask_id):
+ *   logits = cond | (1 + cfg) * cond - cfg * uncond            (:156 / :162; uncond nullable, rows [N, C], bf16 at every op)
+ *   sample = argmax(logits / tau + g(gumbel_u))  | argmax(logits) when gumbel_u is NULL (tau == 0)   (generation_utils.py:37-42)
+ *   conf   = softmax(logits)[sample] (bf16)                                                          (:173-174)
+ *   ids[pos] = sample + vq_offset; then positions with log(clamp_min(conf,1e-20)) + temperature * g(conf_u) strictly below the
+ *   keep_n-th smallest (keep_n clamped to [0, N-1]) are set back to mask_id                          (generation_utils.py:45-61)
+ * g(u) = -log(-log(u + 1e-20) + 1e-20) in bf16. Workspaces: sampled_ws int32 [N], selp_ws float [N], unknown_ws uint8 [N];
+ * masking_out (nullable) uint8 [N]. */
+MMDP_API int mmdp_image_step_t2i(const uint16_t* cond, const uint16_t* uncond, int64_t ld, int N, int C, float cfg,
+                        const uint16_t* gumbel_u, float tau, const uint16_t* conf_u, float temperature, int keep_n,
+                        int64_t* ids, const int32_t* pos, int64_t mask_id, int64_t vq_offset, int32_t* sampled_ws,
+                        float* selp_ws, uint8_t* unknown_ws, uint8_t* masking_out, void* stream);
 MMDP_API int mmdp_image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
                       const uint16_t* conf_noise, float temp, int sched_len, int64_t* ids, const int32_t* pos,
                       int64_t mask_id, int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, void* stream);

@@ -75,6 +75,8 @@ SIGNATURES = {
     "mmdp_rmsnorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mmdp_embed": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
     "mmdp_text_step": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _i64, _f, _vp, _i64, _i, _vp, _vp, _vp]),
+    "mmdp_text_step_gumbel64": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _i64, _f, _vp, _i64, _i, _vp, _vp, _vp]),
+    "mmdp_image_step_t2i": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _f, _vp, _f, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mmdp_image_step": (
         _i,
         [_i, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _f, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -123,6 +123,23 @@ MMDP_API int mmdp_text_step(const uint16_t* cond, const uint16_t* uncond, int64_
                      temperature, ids_text, mask_id, k, x0_ws, conf_ws, (cudaStream_t)stream);
 }
 
+MMDP_API int mmdp_text_step_gumbel64(const uint16_t* cond, const uint16_t* uncond, int64_t ld, int R, int V, float text_cfg,
+                            const double* unoise64, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
+                            int k, int64_t* x0_ws, double* conf_ws, void* stream) {
+    if (!unoise64) return set_error("mmdp_text_step_gumbel64: noise pointer is null");
+    return text_step((const bf16*)cond, (const bf16*)uncond, ld, R, V, text_cfg, nullptr, ld_noise, temperature, ids_text, mask_id, k,
+                     x0_ws, conf_ws, (cudaStream_t)stream, unoise64);
+}
+
+MMDP_API int mmdp_image_step_t2i(const uint16_t* cond, const uint16_t* uncond, int64_t ld, int N, int C, float cfg,
+                        const uint16_t* gumbel_u, float tau, const uint16_t* conf_u, float temperature, int keep_n,
+                        int64_t* ids, const int32_t* pos, int64_t mask_id, int64_t vq_offset, int32_t* sampled_ws,
+                        float* selp_ws, uint8_t* unknown_ws, uint8_t* masking_out, void* stream) {
+    return image_step_t2i((const bf16*)cond, (const bf16*)uncond, ld, N, C, cfg, (const bf16*)gumbel_u, tau, (const bf16*)conf_u,
+                          temperature, keep_n, ids, pos, mask_id, vq_offset, sampled_ws, selp_ws, unknown_ws, masking_out,
+                          (cudaStream_t)stream);
+}
+
 MMDP_API int mmdp_image_step(int variant, const uint16_t* cond, const uint16_t* unc_a, const uint16_t* unc_b, int64_t ld, int N,
                     int C, float s_a, float s_b, const uint16_t* qnoise, const uint16_t* conf_noise, float temp,
                     int sched_len, int64_t* ids, const int32_t* pos, int64_t mask_id, int64_t vq_offset,

@@ -132,7 +132,7 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
 
 int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int R, int V, float text_cfg,
               const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
-              int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream);
+              int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream, const double* unoise64 = nullptr);
 int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_a, const __nv_bfloat16* unc_b, int64_t ld,
                int N, int C, float s_a, float s_b, const __nv_bfloat16* qnoise, const __nv_bfloat16* conf_noise,
                float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset,
@@ -140,7 +140,11 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
                int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream);
 int image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
                  const __nv_bfloat16* conf_noise, float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id,
-                 int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream);
+                 int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream, int k_direct = -1);
+int image_step_t2i(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int N, int C, float cfg,
+                   const __nv_bfloat16* gumbel_u, float tau, const __nv_bfloat16* conf_u, float temperature, int keep_n,
+                   int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset, int32_t* sampled_ws, float* selp_ws,
+                   uint8_t* unknown_ws, uint8_t* masking_out, cudaStream_t stream);
 int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream_t stream);
 
 }  // namespace mmdp

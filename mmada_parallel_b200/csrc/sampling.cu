@@ -25,6 +25,8 @@ struct TextRowArgs {
     const __nv_bfloat16* cond;    // [R, ld]
     const __nv_bfloat16* uncond;  // nullable; M: logits = cond + cfg * (uncond - cond), every op rounded to bf16
     const __nv_bfloat16* unoise;  // nullable; A gumbel: uniform noise [R, V] bf16 (torch.rand(dtype=bf16))
+    const double* unoise64;       // nullable; M gumbel: uniform noise [R, V] fp64 (torch.rand_like(dtype=float64)), key =
+                                  //   exp(logit) / (-log u)^temperature in fp64 (M/models/modeling_mmada.py:49-60)
     int64_t ld, ld_noise;
     int V;
     float cfg, temperature;
@@ -39,14 +41,17 @@ __device__ __forceinline__ float text_logit(float c, float u, float cfg, bool ha
     return bf16_round(__fadd_rn(c, s));
 }
 // logits + temperature * (-log(-log(u + 1e-10) + 1e-10)), all in bf16 (parallel_generator.py:8-20)
+// g = -log(-log(u + eps) + eps), every op rounded to bf16 (eps = 1e-10: parallel_generator.py:8-20; 1e-20: utils/generation_utils.py:28-34)
+__device__ __forceinline__ float gumbel_g_bf16(float u, float eps) {
+    float t = bf16_round(__fadd_rn(u, eps));
+    t = bf16_round(logf(t));
+    t = -t;
+    t = bf16_round(__fadd_rn(t, eps));
+    t = bf16_round(logf(t));
+    return -t;
+}
 __device__ __forceinline__ float gumbel_bf16(float logit, float u, float temperature) {
-    float t = bf16_round(__fadd_rn(u, 1e-10f));
-    t = bf16_round(logf(t));
-    t = -t;
-    t = bf16_round(__fadd_rn(t, 1e-10f));
-    t = bf16_round(logf(t));
-    t = -t;
-    t = bf16_round(__fmul_rn(t, temperature));
+    const float t = bf16_round(__fmul_rn(gumbel_g_bf16(u, 1e-10f), temperature));
     return bf16_round(__fadd_rn(logit, t));
 }
 
@@ -58,12 +63,50 @@ __global__ void __launch_bounds__(kThreads) text_rows_kernel(TextRowArgs a) {
     const uint4* n4 = a.unoise ? reinterpret_cast<const uint4*>(a.unoise + (size_t)row * a.ld_noise) : nullptr;
     const int nvec = a.V / 8;
     const bool has_u = u4 != nullptr, has_n = n4 != nullptr;
+    const double* n64 = a.unoise64 ? a.unoise64 + (size_t)row * a.ld_noise : nullptr;
 
     // pass 1: max of the (CFG-mixed) logits, argmax of the (optionally Gumbel-perturbed) logits
     float mx = -INFINITY;         // softmax max (un-noised)
     float best = -INFINITY;       // argmax key
     int best_i = 0x7fffffff;
     float best_logit = 0.f;       // un-noised logit at best_i
+    if (n64) {
+        // fp64 Gumbel-max of variant M: key = exp(double(l)) / (-log u)^T, first maximal index. The key is kept in fp64
+        // (two floats would lose the tie behaviour); reduced across the CTA below through shared memory.
+        double best_d = -INFINITY;
+        const double T = (double)a.temperature;
+        for (int i = threadIdx.x; i < nvec; i += kThreads) {
+            float c[8], u[8];
+            unpack8(c4[i], c);
+            if (has_u) unpack8(u4[i], u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float l = text_logit(c[j], has_u ? u[j] : 0.f, a.cfg, has_u);
+                mx = fmaxf(mx, l);
+                const double key = exp((double)l) / pow(-log(n64[(size_t)i * 8 + j]), T);
+                if (key > best_d) { best_d = key; best_i = i * 8 + j; best_logit = l; }
+            }
+        }
+        __shared__ double s_kd[kThreads / 32];
+        __shared__ int s_ki[kThreads / 32];
+        __shared__ float s_kl[kThreads / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best_d, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            const float ol = __shfl_xor_sync(0xffffffffu, best_logit, o);
+            if (ob > best_d || (ob == best_d && oi < best_i)) { best_d = ob; best_i = oi; best_logit = ol; }
+        }
+        if ((threadIdx.x & 31) == 0) { s_kd[threadIdx.x >> 5] = best_d; s_ki[threadIdx.x >> 5] = best_i; s_kl[threadIdx.x >> 5] = best_logit; }
+        __syncthreads();
+        best_d = s_kd[0]; best_i = s_ki[0]; best_logit = s_kl[0];
+        for (int i = 1; i < kThreads / 32; ++i)
+            if (s_kd[i] > best_d || (s_kd[i] == best_d && s_ki[i] < best_i)) { best_d = s_kd[i]; best_i = s_ki[i]; best_logit = s_kl[i]; }
+        __syncthreads();
+        // hand the winner to the common reduction below as the only candidate of thread 0 (keys there are floats)
+        best = threadIdx.x == 0 ? 1.0f : -INFINITY;
+        if (threadIdx.x != 0) best_i = 0x7fffffff;
+    } else
     for (int i = threadIdx.x; i < nvec; i += kThreads) {
         float c[8], u[8], n[8];
         unpack8(c4[i], c);
@@ -146,13 +189,14 @@ __global__ void __launch_bounds__(1024) text_commit_kernel(const int64_t* __rest
 
 int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int R, int V, float text_cfg,
               const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,
-              int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream) {
+              int k, int64_t* x0_ws, double* conf_ws, cudaStream_t stream, const double* unoise64) {
     if (R <= 0) return 0;
+    if (unoise && unoise64) return set_error("text_step: bf16 and fp64 Gumbel noise are mutually exclusive");
     if (R > kTextMaxR) return set_error("text_step: at most %d text positions", kTextMaxR);
     if ((V % 8) || (ld % 8) || (unoise && (ld_noise % 8))) return set_error("text_step: V/ld must be multiples of 8");
-    TextRowArgs a{cond, uncond, unoise, ld, ld_noise, V, text_cfg, temperature, x0_ws, conf_ws};
+    TextRowArgs a{cond, uncond, unoise, unoise64, ld, ld_noise, V, text_cfg, temperature, x0_ws, conf_ws};
     {
-        LaunchScope ls(LK_SAMPLE, (double)R * V * 2 * (uncond ? 2 : 1) + (unoise ? (double)R * V * 2 : 0), stream);  // bytes read
+        LaunchScope ls(LK_SAMPLE, (double)R * V * 2 * (uncond ? 2 : 1) + (unoise ? (double)R * V * 2 : 0) + (unoise64 ? (double)R * V * 8 : 0), stream);  // bytes read
         text_rows_kernel<512><<<R, 512, 0, stream>>>(a);
     }
     MMDP_CUDA(cudaGetLastError());
@@ -175,6 +219,9 @@ struct ImageRowArgs {
     int variant;     // 0 = A, 1 = M
     float s_a, s_b;
     const __nv_bfloat16* qnoise;  // nullable: Exp(1) noise [N, C] bf16 (torch.multinomial's q); null -> argmax(probs)
+    const __nv_bfloat16* gumbel_u;  // nullable: uniform noise [N, C] bf16 -> Gumbel-max on the LOGITS, argmax(l / tau + g)
+    float gumbel_tau;               //   (A/utils/generation_utils.py:37-42); sample_logits != 0 with gumbel_u null = argmax(l)
+    int sample_logits;              // 0: sample from the bf16 probabilities (argmax | exponential race); 1: from the logits
     const int64_t* ids;           // full id buffer
     const int* pos;               // [N] sequence position of VQ token r
     int64_t mask_id, vq_offset;
@@ -197,14 +244,19 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
 
     float x[kImgMaxPer][8];
     float mx = -INFINITY;
+    // logits-domain sampling (generate_image): the key is formed here, where the mixed logit is at hand
+    const uint4* g4 = a.gumbel_u ? reinterpret_cast<const uint4*>(a.gumbel_u + (size_t)r * a.C) : nullptr;
+    float lbest = -INFINITY;
+    int lbest_i = 0x7fffffff;
 #pragma unroll
     for (int t = 0; t < kImgMaxPer; ++t) {
         const int i = threadIdx.x + t * kImgThreads;
         if (i < nvec) {
-            float c[8], ua[8], ub[8];
+            float c[8], ua[8], ub[8], gu[8];
             unpack8(c4[i], c);
             if (ua4) unpack8(ua4[i], ua);
             if (ub4) unpack8(ub4[i], ub);
+            if (g4) unpack8(g4[i], gu);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float l = c[j];
@@ -220,6 +272,11 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
                 }
                 x[t][j] = l;
                 mx = fmaxf(mx, l);
+                if (a.sample_logits) {
+                    // (logits / tau + g).argmax(): bf16 at every op; tau == 0 is the plain argmax of the logits
+                    const float key = g4 ? bf16_round(__fadd_rn(bf16_round(__fdiv_rn(l, a.gumbel_tau)), gumbel_g_bf16(gu[j], 1e-20f))) : l;
+                    if (key > lbest) { lbest = key; lbest_i = i * 8 + j; }
+                }
             }
         } else {
 #pragma unroll
@@ -273,8 +330,12 @@ __global__ void __launch_bounds__(kImgThreads) image_rows_kernel(ImageRowArgs a)
             for (int j = 0; j < 8; ++j) {
                 const float p = bf16_round(__fdiv_rn(x[t][j], sum));
                 x[t][j] = p;
-                const float key = q4 ? bf16_round(__fdiv_rn(p, q[j])) : p;
-                if (key > best) { best = key; best_i = i * 8 + j; best_p = p; }
+                if (a.sample_logits) {
+                    if (i * 8 + j == lbest_i) { best = lbest; best_i = lbest_i; best_p = p; }
+                } else {
+                    const float key = q4 ? bf16_round(__fdiv_rn(p, q[j])) : p;
+                    if (key > best) { best = key; best_i = i * 8 + j; best_p = p; }
+                }
             }
             if (a.probs_out) {
 #pragma unroll
@@ -325,6 +386,8 @@ struct RemaskArgs {
     int64_t mask_id, vq_offset;
     int32_t* mask_len_out;       // nullable debug
     uint8_t* masking_out;        // nullable debug [N]
+    int k_direct;                // >= 0: the number of the cut-off element is given (clamped to [0, N-1]) instead of the
+                                 //   max(1, min(unknown - 1, sched_len)) rule (generate_image passes keep_n, :99-103)
 };
 
 __device__ __forceinline__ float log_bf16(float x) { return bf16_round(logf(x)); }
@@ -352,7 +415,7 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
             const float lp = log_bf16(bf16_round(__fadd_rn(p, 1e-10f)));
             const float tn = a.noise ? bf16_round(__fmul_rn(nz, a.temp)) : 0.f;
             conf[t] = bf16_round(__fadd_rn(lp, tn));
-        } else {
+        } else if (a.variant == 1) {
             // confidence = log(clamp(p,1e-20)) + temperature * (-log(clamp(-log(clamp(u,1e-20)),1e-20)))  (sampling.py:9-16,31-32)
             const float lp = log_bf16(fmaxf(p, bf16_round(1e-20f)));
             float g = 0.f;
@@ -362,6 +425,12 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
                 g = log_bf16(fmaxf(g, bf16_round(1e-20f)));
                 g = -g;
             }
+            const float tn = bf16_round(__fmul_rn(g, a.temp));
+            conf[t] = bf16_round(__fadd_rn(lp, tn));
+        } else {
+            // variant 2 (A/utils/generation_utils.py:45-61): log(clamp_min(p,1e-20)) + temperature * (-log(-log(u+1e-20)+1e-20))
+            const float lp = log_bf16(fmaxf(p, bf16_round(1e-20f)));
+            const float g = a.noise ? gumbel_g_bf16(nz, 1e-20f) : 0.f;
             const float tn = bf16_round(__fmul_rn(g, a.temp));
             conf[t] = bf16_round(__fadd_rn(lp, tn));
         }
@@ -376,7 +445,8 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
     // mask_len = max(1, min(unknown - 1, sched_len))
     int k = a.sched_len < unknown_cnt - 1 ? a.sched_len : unknown_cnt - 1;
     if (k < 1) k = 1;
-    if (a.variant == 0) { if (k > a.N - 1) k = a.N - 1; if (k < 0) k = 0; }  // mask_by_random_topk clamps to [0, N-1]
+    if (a.k_direct >= 0) k = a.k_direct;
+    if (a.variant == 0 || a.k_direct >= 0) { if (k > a.N - 1) k = a.N - 1; if (k < 0) k = 0; }  // mask_by_random_topk clamps to [0, N-1]
     int rank[kRemaskPer];
 #pragma unroll
     for (int t = 0; t < kRemaskPer; ++t) {
@@ -406,10 +476,10 @@ __global__ void __launch_bounds__(1024) image_remask_kernel(RemaskArgs a) {
 
 int image_remask(int variant, int N, const int32_t* sampled, const float* selp, const uint8_t* unknown,
                  const __nv_bfloat16* conf_noise, float temp, int sched_len, int64_t* ids, const int* pos, int64_t mask_id,
-                 int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream) {
+                 int64_t vq_offset, int32_t* mask_len_out, uint8_t* masking_out, cudaStream_t stream, int k_direct) {
     if (N <= 0 || N > kRemaskMaxN) return set_error("image_remask: N must be in [1, %d]", kRemaskMaxN);
     RemaskArgs ma{N, variant, sampled, selp, unknown, conf_noise, temp, sched_len, ids, pos, mask_id, vq_offset,
-                  mask_len_out, masking_out};
+                  mask_len_out, masking_out, k_direct};
     LaunchScope ls(LK_SAMPLE, (double)N * 24, stream);
     image_remask_kernel<<<1, 1024, N * sizeof(float), stream>>>(ma);
     MMDP_CUDA(cudaGetLastError());
@@ -425,7 +495,7 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
     if (C <= 0 || (C % 8) || C > kImgThreads * kImgMaxPer * 8) return set_error("image_step: codebook size must be a multiple of 8 and <= 8192");
     if (ld % 8) return set_error("image_step: ld must be a multiple of 8");
     if (variant == 1 && !unc_a) return set_error("image_step: variant M needs uncond logits");
-    ImageRowArgs ra{cond, unc_a, unc_b, ld, C, variant, s_a, s_b, qnoise, ids, pos, mask_id, vq_offset,
+    ImageRowArgs ra{cond, unc_a, unc_b, ld, C, variant, s_a, s_b, qnoise, nullptr, 0.f, 0, ids, pos, mask_id, vq_offset,
                     variant == 0 ? 1 : 0, sampled_ws, selp_ws, unknown_ws, probs_out};
     {
         const int nt = 1 + (unc_a ? 1 : 0) + (unc_b ? 1 : 0) + (qnoise ? 1 : 0);
@@ -435,6 +505,30 @@ int image_step(int variant, const __nv_bfloat16* cond, const __nv_bfloat16* unc_
     MMDP_CUDA(cudaGetLastError());
     return image_remask(variant, N, sampled_ws, selp_ws, unknown_ws, conf_noise, temp, sched_len, ids, pos, mask_id,
                         vq_offset, mask_len_out, masking_out, stream);
+}
+
+// One step of A's MaskGit text-to-image decoding (generators/image_generation_generator.py:119-208) on the N currently
+// masked positions `pos` (compacted by the caller): logits = cond | (1 + s) cond - s uncond, Gumbel-max sample on the logits
+// (utils/generation_utils.py:37-42), confidence = softmax probability of the sample, write-back, then re-mask every
+// position whose noisy log-confidence is below the keep_n-th smallest (generation_utils.py:45-61).
+int image_step_t2i(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int N, int C, float cfg,
+                   const __nv_bfloat16* gumbel_u, float tau, const __nv_bfloat16* conf_u, float temperature, int keep_n,
+                   int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset, int32_t* sampled_ws, float* selp_ws,
+                   uint8_t* unknown_ws, uint8_t* masking_out, cudaStream_t stream) {
+    if (N <= 0 || N > kRemaskMaxN) return set_error("image_step_t2i: N must be in [1, %d]", kRemaskMaxN);
+    if (C <= 0 || (C % 8) || C > kImgThreads * kImgMaxPer * 8) return set_error("image_step_t2i: codebook size must be a multiple of 8 and <= 8192");
+    if (ld % 8) return set_error("image_step_t2i: ld must be a multiple of 8");
+    if (gumbel_u && tau == 0.f) return set_error("image_step_t2i: Gumbel noise given with tau == 0");
+    // CFG mix = variant M's formula with s_a = s (python float), s_b = 1 + s evaluated on the host in double like the reference
+    ImageRowArgs ra{cond, uncond, nullptr, ld, C, uncond ? 1 : 0, cfg, (float)(1.0 + (double)cfg), nullptr, gumbel_u, tau, 1, ids, pos,
+                    mask_id, vq_offset, 0, sampled_ws, selp_ws, unknown_ws, nullptr};
+    {
+        LaunchScope ls(LK_SAMPLE, (double)N * C * 2 * (1 + (uncond ? 1 : 0) + (gumbel_u ? 1 : 0)), stream);
+        image_rows_kernel<<<N, kImgThreads, 0, stream>>>(ra);
+    }
+    MMDP_CUDA(cudaGetLastError());
+    return image_remask(2, N, sampled_ws, selp_ws, unknown_ws, conf_u, temperature, 0, ids, pos, mask_id, vq_offset, nullptr,
+                        masking_out, stream, keep_n < 0 ? 0 : keep_n);
 }
 
 }  // namespace mmdp

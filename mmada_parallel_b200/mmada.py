@@ -54,10 +54,8 @@ class MMadaModelLM(LLaDAForMultiModalGeneration):
             raise ValueError("text_cfg and image_cfg cannot be both 0")                      # :181-182
         if remasking != "low_confidence":
             raise NotImplementedError(remasking)
-        if text_temperature != 0:
-            raise NotImplementedError("M's text Gumbel path (fp64, global RNG, modeling_mmada.py:49-60) is not on the "
-                                      "B200 hot path; the reference default is text_temperature=0")
         uni_prompting = kwargs.get("uni_prompting", None)
+        _text_noise = kwargs.get("_text_noise", None)   # tests: injects the fp64 uniform noise instead of the global-RNG draw
         dev = self.device
         mask_id = int(self.config.mask_token_id)
         n_vq = int(config.model.mmada.num_vq_tokens)
@@ -100,9 +98,18 @@ class MMadaModelLM(LLaDAForMultiModalGeneration):
             self.forward_rows(both, rows_a=rows_text, out_a=text_logits, rows_b=rows_img if is_img else None,
                               col0_b=tvoc, ncols_b=C, out_b=img_logits if is_img else None)     # :172
             # text step on the CFG-mixed logits (:179-209); only the cond row's ids change ...
-            check(lib.mmdp_text_step(ptr(text_logits), text_logits.data_ptr() + max_seq * V * 2, V, max_seq, V,
-                                     float(text_cfg), None, 0, 0.0, both.data_ptr() + t0 * 8, mask_id,
-                                     int(num_transfer[i]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+            if text_temperature != 0:
+                # add_gumbel_noise (:49-60): fp64 uniform noise of the text-logits shape from the GLOBAL RNG of the logits'
+                # device - the same call the reference makes on a GPU, so the same Philox stream is consumed
+                u64 = (_text_noise(i, (1, max_seq, V)) if _text_noise is not None
+                       else torch.rand((1, max_seq, V), dtype=torch.float64, device=dev)).to(dev).contiguous()
+                check(lib.mmdp_text_step_gumbel64(ptr(text_logits), text_logits.data_ptr() + max_seq * V * 2, V, max_seq, V,
+                                                  float(text_cfg), ptr(u64), V, float(text_temperature), both.data_ptr() + t0 * 8,
+                                                  mask_id, int(num_transfer[i]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+            else:
+                check(lib.mmdp_text_step(ptr(text_logits), text_logits.data_ptr() + max_seq * V * 2, V, max_seq, V,
+                                         float(text_cfg), None, 0, 0.0, both.data_ptr() + t0 * 8, mask_id,
+                                         int(num_transfer[i]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
             # ... and the uncond row shares the generated suffix (:166-169)
             both[1, P:] = both[0, P:]
             if not is_img:
@@ -135,14 +142,14 @@ class MMadaModelLM(LLaDAForMultiModalGeneration):
         kernel per batch row: logits = un + (cfg + 1) * (l - un) in bf16 (:660), argmax, fp64 softmax confidence, the k
         most confident masked positions committed (:676-683). Positions after the block carry confidence -inf in the
         reference (:673) and earlier blocks are complete, so only the block's rows are evaluated.
-        Not built (raise): padding masks (`attention_mask` with zeros -> attention_bias), `temperature > 0` (fp64 Gumbel from
-        the global RNG, :49-60), `remasking='random'` (global RNG), `input_embeddings`."""
+        `attention_mask`: the reference turns a mask with zeros into an `attention_bias` (:626-627) that the M backbone never
+        reads (its blocks take `attention_mask`, which stays None) - padding is NOT masked there, so the argument is accepted
+        and has no effect (pinned against the real reference in oracle/make_golden_m_modes.py).
+        `temperature > 0`: fp64 Gumbel-max (:49-60); the uniform noise has the FULL logits shape [B', L, V] and comes from the
+        global RNG of the logits' device, drawn here with the same call (same stream as the reference on a GPU).
+        Not built (raise): `remasking='random'` (global RNG), `input_embeddings`."""
         if idx is None or input_embeddings is not None:
             raise NotImplementedError("mmu_generate: only token-id prompts (idx) are supported")
-        if attention_mask is not None and bool((attention_mask == 0).any()):
-            raise NotImplementedError("mmu_generate: padding masks (attention_bias) are not supported by the native attention")
-        if temperature != 0:
-            raise NotImplementedError("mmu_generate: temperature > 0 draws fp64 Gumbel noise from the global RNG in the reference")
         if remasking != "low_confidence":
             raise NotImplementedError(remasking)
         dev = self.device
@@ -170,18 +177,101 @@ class MMadaModelLM(LLaDAForMultiModalGeneration):
                               for r in range(nb)])
             for i in range(steps):
                 self.forward_rows(both, rows_a=rows, out_a=text_logits)
+                u64 = None
+                if temperature != 0:
+                    # rand_like(logits [B, L, V], dtype=float64): the whole sequence's noise is drawn (keeps the RNG stream
+                    # aligned with the reference); only the current block's rows are read by the kernel
+                    u64 = (self._mmu_noise(blk * steps + i, (B, L, V)) if getattr(self, "_mmu_noise", None) is not None
+                           else torch.rand((B, L, V), dtype=torch.float64, device=dev)).to(dev).contiguous()
                 for j in range(B):
                     cond = text_logits.data_ptr() + j * block_length * V * 2
-                    if use_cfg:
-                        unc = text_logits.data_ptr() + (B + j) * block_length * V * 2
-                        # kernel: c + cfg * (u - c) with c = un-logits, u = cond logits, cfg = cfg_scale + 1
-                        check(lib.mmdp_text_step(unc, cond, V, block_length, V, float(cfg_scale + 1), None, 0, 0.0,
-                                                 both.data_ptr() + (j * L + bs) * 8, int(mask_id), int(num_transfer[i]),
-                                                 ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+                    unc = text_logits.data_ptr() + (B + j) * block_length * V * 2 if use_cfg else None
+                    # kernel: c + cfg * (u - c) with c = un-logits, u = cond logits, cfg = cfg_scale + 1
+                    a0, a1, cf = (unc, cond, float(cfg_scale + 1)) if use_cfg else (cond, None, 0.0)
+                    ids_ptr = both.data_ptr() + (j * L + bs) * 8
+                    if u64 is not None:
+                        check(lib.mmdp_text_step_gumbel64(a0, a1, V, block_length, V, cf, u64.data_ptr() + (j * L + bs) * V * 8, V,
+                                                          float(temperature), ids_ptr, int(mask_id), int(num_transfer[i]),
+                                                          ptr(x0_ws), ptr(conf_ws), stream_ptr()))
                     else:
-                        check(lib.mmdp_text_step(cond, None, V, block_length, V, 0.0, None, 0, 0.0,
-                                                 both.data_ptr() + (j * L + bs) * 8, int(mask_id), int(num_transfer[i]),
-                                                 ptr(x0_ws), ptr(conf_ws), stream_ptr()))
+                        check(lib.mmdp_text_step(a0, a1, V, block_length, V, cf, None, 0, 0.0, ids_ptr, int(mask_id),
+                                                 int(num_transfer[i]), ptr(x0_ws), ptr(conf_ws), stream_ptr()))
                 if use_cfg:
                     both[B:, P:] = both[:B, P:]
         return both[:B].clone()
+
+    @torch.no_grad()
+    def t2i_generate(
+        self,
+        input_ids: torch.LongTensor = None,
+        uncond_input_ids: torch.LongTensor = None,
+        attention_mask=None,
+        uncond_attention_mask=None,
+        temperature=1.0,
+        timesteps=18,
+        guidance_scale=0,
+        noise_schedule=cosine_schedule,
+        generator: torch.Generator = None,
+        config=None,
+        seq_len=1024,
+        mask_token_id=126336,
+        resolution=512,
+        codebook_size=8192,
+        **kwargs,
+    ):
+        """MaskGit text-to-image decoding of variant M (modeling_mmada.py:265-359): the last seq_len + 1 positions of
+        `input_ids [B, L]` hold the image tokens followed by one closing token. Per step: one forward over [input_ids] or, with
+        guidance, over the batch [input_ids; uncond_prefix + input_ids[:, resolution + 1:]] with the LM head restricted to the
+        image rows x the codebook window; then per batch row the variant-M image-step kernel (CFG mix (1 + s) c - s u, softmax,
+        torch.multinomial's exponential race, confidence, Gumbel re-mask with the strict cut-off). Kept from the reference:
+        `input_ids` is updated IN PLACE (:355); `temperature` is multiplied by (1 - ratio) on every step, i.e. it compounds
+        (:352); the attention masks only build an attention_bias the backbone never reads (no effect; pinned in
+        oracle/make_golden_m_modes.py). Returns the last step's sampled ids [B, seq_len] (before re-masking)."""
+        uni_prompting = kwargs.get("uni_prompting", None)
+        dev = self.device
+        n, C = int(seq_len), int(codebook_size)
+        tvoc = len(uni_prompting.text_tokenizer)
+        caller_ids = input_ids
+        ids = input_ids.to(device=dev, dtype=torch.int64).clone().contiguous()
+        B, L = ids.shape
+        use_cfg = uncond_input_ids is not None and guidance_scale > 0
+        nb = 2 * B if use_cfg else B
+        if nb > self.max_batch:
+            raise ValueError(f"t2i_generate: batch {nb} (incl. the guidance copy) exceeds the model's max_batch={self.max_batch}")
+        both = torch.empty((nb, L), dtype=torch.int64, device=dev)
+        if use_cfg:
+            unc_prefix = uncond_input_ids.to(device=dev, dtype=torch.int64)[:, : resolution + 1]           # :298
+            if unc_prefix.shape[1] != resolution + 1 or unc_prefix.shape[0] != B:
+                raise ValueError("t2i_generate: uncond_input_ids must be [B, >= resolution + 1]")
+        p0 = L - (n + 1)
+        pos = torch.arange(p0, p0 + n, dtype=torch.int32, device=dev)
+        rows = torch.cat([pos + r * L for r in range(nb)])
+        logits = torch.empty((nb * n, C), dtype=torch.bfloat16, device=dev)
+        sampled_ws = torch.zeros((B, n), dtype=torch.int32, device=dev)
+        selp_ws = torch.empty(n, dtype=torch.float32, device=dev)
+        unk_ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        noise = _Noise(generator, dev)
+        for step in range(timesteps):
+            both[:B] = ids
+            if use_cfg:
+                both[B:, : resolution + 1] = unc_prefix                                                    # :304-305
+                both[B:, resolution + 1:] = ids[:, resolution + 1:]
+            self.forward_rows(both, rows_b=rows, col0_b=tvoc, ncols_b=C, out_b=logits)                     # :309 / :319
+            q = noise.exponential((B * n, C))                                                              # multinomial over [B*n, C] (:327)
+            ratio = 1.0 * (step + 1) / timesteps
+            temperature = temperature * (1.0 - ratio)                                                      # :352 (compounds)
+            un = torch.zeros((B, n), dtype=torch.bfloat16, device=noise.gdev).uniform_(0, 1, generator=generator).to(dev)
+            for b in range(B):
+                cond = logits.data_ptr() + b * n * C * 2
+                # no guidance: (1 + 0) * cond - 0 * cond == cond in bf16, the kernel's variant-M mix with itself as "uncond"
+                unc = logits.data_ptr() + (B + b) * n * C * 2 if use_cfg else cond
+                s = float(guidance_scale) if use_cfg else 0.0
+                check(lib.mmdp_image_step(1, cond, unc, None, C, n, C, s, float(1 + s), q.data_ptr() + b * n * C * 2,
+                                          un.data_ptr() + b * n * 2, float(temperature),
+                                          scheduled_mask_len(n, step, timesteps, noise_schedule), ids.data_ptr() + b * L * 8,
+                                          ptr(pos), int(mask_token_id), tvoc, sampled_ws.data_ptr() + b * n * 4, ptr(selp_ws),
+                                          ptr(unk_ws), None, None, None, stream_ptr()))
+        if torch.is_tensor(caller_ids):
+            caller_ids.copy_(ids.to(caller_ids.device))                                                    # in-place update, like the reference
+        self.raise_device_errors()
+        return sampled_ws.to(torch.int64)

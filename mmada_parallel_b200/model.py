@@ -167,6 +167,20 @@ class LLaDAForMultiModalGeneration:
     def to(self, *_a, **_k):
         return self
 
+    def parameters(self):
+        """The reference's generators probe the device with `next(model.parameters()).device` (image_generation_generator.py:54)."""
+        yield torch.empty(0, dtype=torch.bfloat16, device=self.device)
+
+    def caching(self, enable: bool = True) -> None:
+        """Mirror of LLaDAModel.caching (modeling_llada.py:1415-1418). The reference's per-block K/V and logit caches only
+        change results when a caller passes `to_compute_mask` / `cat` to LLaDAModelLM.forward; no caller in the reference does
+        (the wrapper's forward cannot, modeling_xllmx_dimoo.py:41-72), so enabling the cache is output-invariant. Nothing
+        is stored here."""
+        self._caching = bool(enable)
+
+    def empty_cache(self) -> None:
+        """Mirror of LLaDAModel.empty_cache (a no-op here, see caching())."""
+
     def raise_device_errors(self) -> None:
         """Reads and clears the sticky device-side error flags of the forwards issued so far (synchronises the stream).
         The kernels never read out of bounds; they flag what torch would have raised for."""
@@ -193,8 +207,9 @@ class LLaDAForMultiModalGeneration:
     def forward(self, input_ids=None, labels=None, infer: bool = False, use_cache: bool = False, **_) -> ModelOutput:
         if labels is not None or not infer:
             raise NotImplementedError("only the inference branch (infer=True) is on the B200 hot path")
-        if use_cache:
-            raise NotImplementedError("use_cache=True (token-cache forward) is out of scope (SURVEY.md §8f rank 4)")
+        # use_cache=True: the reference then STORES K/V/logits per block (modeling_llada.py:929-940, :1406-1413) and returns the
+        # same logits - partial recompute needs `to_compute_mask`, which this call signature (like the reference wrapper's,
+        # modeling_xllmx_dimoo.py:41-72) does not have. Accepted and output-invariant; see caching().
         ids = self._ids_device(input_ids)
         B, L = ids.shape
         logits = torch.empty((B, L, self.vocab_rows), dtype=torch.bfloat16, device=self.device)

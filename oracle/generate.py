@@ -204,14 +204,14 @@ def generate_ti2ti_stepwise(model, input_ids, text_start, text_end, image_start,
 def interleave_generate(model, input_ids, uncond_input_ids, text_cfg, image_cfg, text_steps, image_steps, soi_id, eoi_id,
                         bos_id, mask_id, num_vq_tokens, codebook_size, max_seq_length, text_vocab_len,
                         noise_schedule=S.cosine_schedule, generator=None, text_temperature=0.0,
-                        image_temperature=1.0, trace: Optional[list] = None):
+                        image_temperature=1.0, trace: Optional[list] = None, text_noise=None):
     """Restates MMadaModelLM.interleave_generate (modeling_mmada.py:118-248) with the config/tokenizer look-ups
     (reserved_token_mapping, config.model.mmada.*, len(uni_prompting.text_tokenizer)) passed as plain integers.
     `model(ids[B,L]).logits`. Returns (image ids [1, num_vq_tokens] (pre-remask sample), text ids [1, max_seq_length])."""
     if not (text_cfg or image_cfg):
         raise ValueError("text_cfg and image_cfg cannot be both 0")
-    if text_temperature != 0:
-        raise NotImplementedError("M add_gumbel_noise draws from the global RNG (modeling_mmada.py:56); not replayable")
+    # text_temperature != 0: add_gumbel_noise draws fp64 noise [1, max_seq_length, V] from the GLOBAL RNG (modeling_mmada.py:56),
+    # replayed here with the same call (seed the global RNG to compare); `text_noise` may inject it instead
     inp, unc = input_ids.unsqueeze(0), uncond_input_ids.unsqueeze(0)
     out_ids = torch.cat([torch.full((1, 1), soi_id), torch.full((1, num_vq_tokens), mask_id), torch.full((1, 1), eoi_id),
                          torch.full((1, 1), bos_id), torch.full((1, max_seq_length - 1), mask_id)], dim=1)  # :142-148
@@ -229,9 +229,13 @@ def interleave_generate(model, input_ids, uncond_input_ids, text_cfg, image_cfg,
         logits = model(torch.cat([ids, unc_ids], dim=0)).logits                     # :172  (B = 2)
         noise.dtype = logits.dtype
         cond_logits, uncond_logits = torch.chunk(logits, 2, dim=0)
+        u64 = None
+        if text_temperature != 0:
+            shape = (1, max_seq_length, logits.shape[-1])
+            u64 = (text_noise(i, shape) if text_noise is not None else torch.rand(shape, dtype=torch.float64, device=logits.device))[0]
         new_ids, x0, conf = S.text_step(cond_logits[0, -max_seq_length:], ids[0, -max_seq_length:], mask_id,
                                         num_transfer[i], uncond_logits=uncond_logits[0, -max_seq_length:],
-                                        text_cfg=text_cfg)
+                                        text_cfg=text_cfg, temperature=text_temperature, uniform64=u64)
         ids[0, -max_seq_length:] = new_ids
         rec = {"step": i, "ids_after_text": ids[0].clone()}
         if i in img_idx:                                                             # :211
@@ -254,15 +258,17 @@ def interleave_generate(model, input_ids, uncond_input_ids, text_cfg, image_cfg,
 
 @torch.no_grad()
 def mmu_generate(model, idx, max_new_tokens=128, steps=128, block_length=128, temperature=0.0, cfg_scale=0.0,
-                 remasking="low_confidence", mask_id=126336, attention_mask=None, trace: Optional[list] = None):
+                 remasking="low_confidence", mask_id=126336, attention_mask=None, trace: Optional[list] = None, text_noise=None):
     """Restates MMadaModelLM.mmu_generate (modeling_mmada.py:619-691): LLaDA block-wise un-masking of `max_new_tokens`
     masks appended to the prompt `idx [B, P]`. `model(ids[B', L]).logits`. Per step: forward (CFG: batch [x; x with the
     prompt masked], logits = un + (cfg + 1) * (l - un)), argmax, fp64 softmax confidence, positions after the current block
     excluded, the k most confident masked positions of each row committed. Returns x [B, P + max_new_tokens]."""
-    if attention_mask is not None and bool((attention_mask == 0).any()):
-        raise NotImplementedError("padding masks (attention_bias) are outside this restatement")
-    if temperature != 0:
-        raise NotImplementedError("add_gumbel_noise draws fp64 noise from the global RNG (modeling_mmada.py:49-60)")
+    # attention_mask: the reference turns a mask with zeros into `attention_bias` (:626-627) and hands it to self(...) only in
+    # the cfg_scale == 0 branch (:663); LLaDAModel.forward of variant M never reads attention_bias (its blocks take
+    # `attention_mask`, which stays None) - padding is NOT masked and the argument cannot change the result. Pinned against
+    # the real reference with a zero-containing mask in oracle/make_golden_mmu.py.
+    # temperature != 0: add_gumbel_noise draws fp64 noise of the FULL logits shape [B, L, V] from the global RNG (:665 -> :56);
+    # the same call is issued here (seed the global RNG to compare), or `text_noise(step_index, shape)` injects it.
     if remasking != "low_confidence":
         raise NotImplementedError(remasking)                                         # 'random' uses the global RNG
     B, P = idx.shape
@@ -284,17 +290,70 @@ def mmu_generate(model, idx, max_new_tokens=128, steps=128, block_length=128, te
                 logits, un_logits = torch.chunk(model(torch.cat([x, un_x], dim=0)).logits, 2, dim=0)
             else:
                 logits, un_logits = model(x).logits, None
+            u64 = None
+            if temperature != 0:
+                shape = tuple(logits.shape)
+                u64 = text_noise(blk * steps + i, shape) if text_noise is not None else torch.rand(shape, dtype=torch.float64, device=logits.device)
             for j in range(B):
                 # positions [be, L) carry confidence -inf (:673): only [0, be) can be selected
+                uj = u64[j, :be] if u64 is not None else None
                 if un_logits is not None:   # un + (cfg + 1) * (l - un)  (:660)
                     new_ids, x0, conf = S.text_step(un_logits[j, :be], x[j, :be], mask_id, num_transfer[j][i],
-                                                    uncond_logits=logits[j, :be], text_cfg=cfg_scale + 1)
+                                                    uncond_logits=logits[j, :be], text_cfg=cfg_scale + 1, temperature=temperature, uniform64=uj)
                 else:
-                    new_ids, x0, conf = S.text_step(logits[j, :be], x[j, :be], mask_id, num_transfer[j][i])
+                    new_ids, x0, conf = S.text_step(logits[j, :be], x[j, :be], mask_id, num_transfer[j][i], temperature=temperature, uniform64=uj)
                 x[j, :be] = new_ids
             if trace is not None:
                 trace.append(x.clone())
     return x
+
+
+@torch.no_grad()
+def t2i_generate(model, input_ids, uncond_input_ids=None, attention_mask=None, uncond_attention_mask=None, temperature=1.0,
+                 timesteps=18, guidance_scale=0, noise_schedule=S.cosine_schedule, generator=None, seq_len=1024,
+                 mask_token_id=126336, resolution=512, codebook_size=8192, text_vocab_len=126349, trace: Optional[list] = None):
+    """Restates MMadaModelLM.t2i_generate (modeling_mmada.py:265-359), MaskGit decoding of the LAST seq_len + 1 positions
+    (image tokens followed by one closing token) of `input_ids [B, L]`, which is updated IN PLACE like the reference's tensor.
+    The attention masks only build an `attention_bias` the M backbone never reads (see mmu_generate): padding is not masked.
+    Quirk kept: `temperature` is multiplied by (1 - ratio) on EVERY step (:341), i.e. it compounds.
+    Returns the last step's sampled ids [B, seq_len] (before re-masking)."""
+    n, tv, C = seq_len, text_vocab_len, codebook_size
+    B = input_ids.shape[0]
+    cur = input_ids[:, -(n + 1):-1].clone()
+    cur = torch.where(cur == mask_token_id, mask_token_id, cur - tv)                      # :293-294
+    if uncond_input_ids is not None:
+        uncond_prefix = uncond_input_ids[:, :resolution + 1]                               # :298
+    noise = S.NoiseSource(generator)
+    sampled_ids = None
+    for step in range(timesteps):
+        if uncond_input_ids is not None and guidance_scale > 0:                            # :302-316
+            uncond_input_ids = torch.cat([uncond_prefix, input_ids[:, resolution + 1:]], dim=1)
+            logits = model(torch.cat([input_ids, uncond_input_ids])).logits
+            cond_logits, uncond_logits = torch.chunk(logits, 2, dim=0)
+            logits = (1 + guidance_scale) * cond_logits - guidance_scale * uncond_logits
+        else:
+            logits = model(input_ids).logits                                               # :318-319
+        logits = logits[:, -(n + 1):-1, tv: tv + C]
+        noise.dtype = logits.dtype
+        probs = logits.softmax(dim=-1)                                                     # :324
+        q = noise.multinomial_q(B * n, C).to(probs.device)                                 # torch.multinomial(probs [B*n, C], 1)  :327
+        sampled_ids = S.sample_rows(probs.reshape(-1, C), q).view(B, n)
+        unknown_map = cur == mask_token_id
+        sampled_ids = torch.where(unknown_map, sampled_ids, cur)                           # :332
+        ratio = 1.0 * (step + 1) / timesteps
+        mask_ratio = noise_schedule(torch.tensor(ratio))
+        selected = torch.gather(probs, -1, sampled_ids.long()[..., None]).squeeze(-1)
+        selected = torch.where(unknown_map, selected, torch.finfo(selected.dtype).max)     # :343
+        mask_len = (n * mask_ratio).floor().unsqueeze(0)
+        mask_len = torch.max(torch.tensor([1]), torch.min(unknown_map.sum(dim=-1, keepdim=True) - 1, mask_len))   # :347-349
+        temperature = temperature * (1.0 - ratio)                                          # :352 (compounds)
+        un = noise.remask_uniform((B, n)).to(probs.device)
+        masking = torch.stack([S.mask_by_random_topk_m(int(mask_len[b]), selected[b], temperature, un[b])[0] for b in range(B)])
+        input_ids[:, -(n + 1):-1] = torch.where(masking, mask_token_id, sampled_ids + tv)  # :355-357
+        cur = torch.where(masking, mask_token_id, sampled_ids)
+        if trace is not None:
+            trace.append(dict(step=step, sampled=sampled_ids.clone(), ids=input_ids.clone(), mask_len=mask_len.clone()))
+    return sampled_ids
 
 
 # ---------------------------------------------------------------------------------------------------------------

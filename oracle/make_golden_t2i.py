@@ -52,10 +52,16 @@ def main():
                       uncon_ids=lay["uncon_ids"], text_vocab_size=126356, codebook_size=8192, **kw)
         with quiet():
             vr = gi.generate_image(ref, lay["prompt"], generator=torch.Generator().manual_seed(seed), use_cache=False, debug=False, **common)
+        # the reference's token cache (use_cache=True): K/V/logits are STORED per block but generate_image never passes
+        # `to_compute_mask`, so nothing is ever re-used - pinned here: identical output with the flag on
+        with quiet():
+            vc = gi.generate_image(ref, lay["prompt"], generator=torch.Generator().manual_seed(seed), use_cache=True, debug=False, **common)
+            ref.caching(False)
+        assert torch.equal(vr, vc), f"generate_image {name}: use_cache=True changed the reference's output"
         trace = []
         vo = G.generate_image(oracle_model, lay["prompt"], generator=torch.Generator().manual_seed(seed), trace=trace, **common)
         assert torch.equal(vr, vo), f"generate_image {name}: oracle != reference"
-        runs.append(dict(name=name, kwargs=kw, seed=seed, vq_ids=vr.clone(), steps_run=len(trace)))
+        runs.append(dict(name=name, kwargs=kw, seed=seed, vq_ids=vr.clone(), steps_run=len(trace), use_cache_invariant=True))
         print("t2i", name, "ok; steps run:", len(trace), "masked left:", int((vr == 126336).sum()))
     torch.save(dict(meta=dict(tiny=TINY, weight_seed=WEIGHT_SEED), layout=lay, runs=runs), os.path.join(OUT, "trajectory_t2i_tiny.pt"))
 

@@ -99,9 +99,20 @@ def add_gumbel_noise_a(logits: torch.Tensor, temperature: float, uniform_noise: 
     return logits + temperature * gumbel_noise
 
 
+def add_gumbel_noise_m(logits: torch.Tensor, temperature: float, uniform64: Optional[torch.Tensor] = None):
+    """M/models/modeling_mmada.py:49-60: fp64 Gumbel-max, exp(logits) / (-log u)^temperature with u = torch.rand_like(logits,
+    dtype=float64) drawn from the GLOBAL RNG of the logits' device (explicit here when `uniform64` is given)."""
+    if temperature == 0:
+        return logits
+    logits = logits.to(torch.float64)
+    noise = torch.rand_like(logits, dtype=torch.float64) if uniform64 is None else uniform64
+    gumbel_noise = (-torch.log(noise)) ** temperature
+    return logits.exp() / gumbel_noise
+
+
 def text_step(text_logits: torch.Tensor, ids_text: torch.Tensor, mask_id: int, k: int,
               uncond_logits: Optional[torch.Tensor] = None, text_cfg: float = 0.0, temperature: float = 0.0,
-              uniform_noise: Optional[torch.Tensor] = None):
+              uniform_noise: Optional[torch.Tensor] = None, uniform64: Optional[torch.Tensor] = None, gumbel_m: bool = False):
     """One text un-masking step for one batch row.
     A: parallel_generator.py:181-217 (logits = cond).  M: modeling_mmada.py:179-209 (logits = cond + cfg*(uncond-cond)).
     text_logits [R, V] (bf16), ids_text [R] int64 (modified copy returned). Returns (new_ids, x0, confidence)."""
@@ -109,7 +120,10 @@ def text_step(text_logits: torch.Tensor, ids_text: torch.Tensor, mask_id: int, k
     if uncond_logits is not None:
         logits = text_logits + text_cfg * (uncond_logits - text_logits)          # modeling_mmada.py:179
     masked = ids_text == mask_id
-    logits_with_noise = add_gumbel_noise_a(logits, temperature, uniform_noise)
+    if gumbel_m or uniform64 is not None:
+        logits_with_noise = add_gumbel_noise_m(logits, temperature, uniform64)       # modeling_mmada.py:185 / :659
+    else:
+        logits_with_noise = add_gumbel_noise_a(logits, temperature, uniform_noise)
     x0 = torch.argmax(logits_with_noise, dim=-1)                                  # :189
     p = F.softmax(logits.to(torch.float64), dim=-1)                              # :193
     x0_p = torch.squeeze(torch.gather(p, dim=-1, index=torch.unsqueeze(x0, -1)), -1)

@@ -183,17 +183,30 @@ def test_full_size_properties():
     L = 2414
     ids = torch.randint(0, 126000, (2, L), device="cuda", generator=g)
     rows = torch.cat([torch.arange(2157, 2413), torch.arange(L + 1100, L + 1100 + 64)]).to(torch.int32).cuda()
+    from mmada_parallel_b200 import _lib
     a2, _ = m.forward_rows(ids, rows_a=rows)
     a2b, _ = m.forward_rows(ids, rows_a=rows)
     assert torch.equal(a2, a2b), "forward must be deterministic"
     a0, _ = m.forward_rows(ids[0:1].contiguous(), rows_a=rows[:256].contiguous())
     a1, _ = m.forward_rows(ids[1:2].contiguous(), rows_a=(rows[256:] - L).contiguous())
-    # batch rows are independent. (The split-K tail of the residual GEMMs partitions K differently for M = 2L and M = L,
-    # so the fp32 summation ORDER - not the rounding points - may differ: equality up to isolated 1-ulp roundings.)
+    # Batch rows are independent. The split-K tails partition K differently for M = 2L and M = L (which tiles fall into the
+    # partial last wave depends on M), so with them the fp32 summation ORDER - not the rounding points - differs and
+    # bf16 roundings flip here and there, which the attention mixes into every row: bounded, not bit-equal ...
     for got, want in ((a2[:256], a0), (a2[256:], a1)):
         d = (got.float() - want.float()).abs()
-        assert d.max() <= 4 * want.float().abs().max() * 2.0 ** -8, float(d.max())
-        assert (got != want).float().mean() < 0.25  # isolated 1-ulp flips propagated through one layer + the head
+        scale = want.float().abs().max()
+        assert d.max() <= 4 * scale * 2.0 ** -8, float(d.max())
+        assert d.mean() <= 0.5 * scale * 2.0 ** -8, float(d.mean())
+    # ... and WITHOUT the split (every tile accumulates K in one fixed order) the CFG batch is bit-identical to two
+    # single forwards: the kernels themselves have no cross-row dependence
+    try:
+        _lib.lib.mmdp_set_gemm_splitk(0)
+        b2, _ = m.forward_rows(ids, rows_a=rows)
+        b0, _ = m.forward_rows(ids[0:1].contiguous(), rows_a=rows[:256].contiguous())
+        b1, _ = m.forward_rows(ids[1:2].contiguous(), rows_a=(rows[256:] - L).contiguous())
+    finally:
+        _lib.lib.mmdp_set_gemm_splitk(2)
+    assert torch.equal(b2[:256], b0) and torch.equal(b2[256:], b1), "batch rows must be independent"
     assert torch.isfinite(a2.float()).all() and a2.float().abs().max() > 0.1
 
 
@@ -255,20 +268,38 @@ def test_full_size_block_and_head_vs_oracle():
         b_o = torch.nn.functional.linear(xn[1100:1100 + 1024], head[126356:126356 + 8192])
     print(f"[full-size oracle] CPU block + heads: {time.time() - t0:.1f} s")
 
-    def check(got, want, what):
-        gq, wq = got.float().cpu(), want.float()
-        scale = wq.abs().max().item()
-        err = (gq - wq).abs()
-        ulp = scale * 2.0 ** -8
-        print(f"[full-size] {what}: scale {scale:.3f}, max err {err.max().item() / ulp:.2f} ulp, mean err {err.mean().item() / ulp:.4f} ulp, "
-              f"bit-equal {float((gq == wq).float().mean()):.4f}")
-        assert torch.isfinite(gq).all(), what
-        assert err.max().item() <= 4 * ulp, (what, err.max().item() / ulp)
-        assert err.mean().item() <= 0.25 * ulp, (what, err.mean().item() / ulp)
+    # The yardstick: the SAME oracle code run by torch eager on this GPU (cuBLAS + SDPA + ATen) differs from the CPU oracle
+    # through accumulation order and the attention's internal precision, exactly as the native kernels do. The native path
+    # must be as close to the CPU oracle as the library path is (x1.5), and inside 4 bf16 ulp of the tensor's scale.
+    with torch.no_grad():
+        wg = sd
+        xg = torch.nn.functional.embedding(ids, wg["model.transformer.wte.weight"])
+        xg = llada.block_forward(xg, wg, p, cfg, pos_sin.cuda(), pos_cos.cuda())
+        xng = llada.rms_norm(xg, wg["model.transformer.ln_f.weight"], cfg.rms_norm_eps)[0]
+        a_e = torch.nn.functional.linear(xng[2157:2413], wg["model.transformer.ff_out.weight"])
+        b_e = torch.nn.functional.linear(xng[1100:1100 + 1024], wg["model.transformer.ff_out.weight"][126356:126356 + 8192])
 
-    check(hidden, x[0], "residual stream after the block")
-    check(a, a_o, "text-row logits")
-    check(b, b_o, "image-row codebook logits")
+    failures = []
+
+    def check(got, eager, want, what):
+        gq, eq, wq = got.float().cpu(), eager.float().cpu(), want.float()
+        scale = wq.abs().max().item()
+        ulp = scale * 2.0 ** -8
+        err, err_e = (gq - wq).abs(), (eq - wq).abs()
+        print(f"[full-size] {what}: scale {scale:.3f} | native vs CPU oracle: max {err.max().item() / ulp:.2f} ulp, mean {err.mean().item() / ulp:.4f} ulp, "
+              f"bit-equal {float((gq == wq).float().mean()):.4f} | torch-eager-on-GPU vs CPU oracle: max {err_e.max().item() / ulp:.2f} ulp, "
+              f"mean {err_e.mean().item() / ulp:.4f} ulp, bit-equal {float((eq == wq).float().mean()):.4f}")
+        if not torch.isfinite(gq).all():
+            failures.append((what, "non-finite"))
+        if err.max().item() > 4 * ulp:
+            failures.append((what, "max", err.max().item() / ulp))
+        if err.mean().item() > 1.5 * err_e.mean().item() + 0.02 * ulp:
+            failures.append((what, "mean vs eager", err.mean().item() / ulp, err_e.mean().item() / ulp))
+
+    check(hidden, xg[0], x[0], "residual stream after the block")
+    check(a, a_e, a_o, "text-row logits")
+    check(b, b_e, b_o, "image-row codebook logits")
+    assert not failures, failures
     # greedy decisions: equal wherever the oracle's own top-1/top-2 margin exceeds twice the bound
     top2 = a_o.float().topk(2, dim=-1).values
     clear = (top2[:, 0] - top2[:, 1]) > 8 * a_o.float().abs().max() * 2.0 ** -8

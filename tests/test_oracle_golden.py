@@ -179,9 +179,8 @@ def test_mmu_generate_matches_reference_golden(tiny):
         out = G.mmu_generate(model, run["idx"], attention_mask=am, **run["kwargs"])
         assert torch.equal(out, run["out"]), run["name"]
     with pytest.raises(NotImplementedError):
-        G.mmu_generate(model, t["runs"][0]["idx"], temperature=0.5)
-    with pytest.raises(NotImplementedError):
-        G.mmu_generate(model, t["runs"][0]["idx"], attention_mask=torch.zeros(1, 152, dtype=torch.long))
+        G.mmu_generate(model, t["runs"][0]["idx"], remasking="random")
+    # (temperature > 0 and zero-containing attention masks: test_variant_m_modes_match_reference_golden)
 
 
 def test_generate_image_t2i_matches_reference_golden(tiny):
@@ -198,3 +197,27 @@ def test_generate_image_t2i_matches_reference_golden(tiny):
         assert torch.equal(out, run["vq_ids"]), run["name"]
         assert len(tr) == run["steps_run"] and out.shape == (1, lay["seq_len"])
         assert int((out < 126356).sum()) == 0 and int((out >= 126356 + 8192).sum()) == 0
+
+
+def test_variant_m_modes_match_reference_golden(tiny):
+    """t2i_generate, mmu_generate (zero-containing attention mask; temperature > 0) and interleave_generate with
+    text_temperature > 0 against the ids the REAL MMadaModelLM produced (oracle/make_golden_m_modes.py)."""
+    _, cfg, sd, model = tiny
+    t = load_golden("trajectory_m_modes_tiny.pt")
+    tv = t["meta"]["text_vocab_len"]
+    for r in t["t2i"]:
+        ids = r["input_ids"].clone()
+        out = G.t2i_generate(model, ids, r["uncond_input_ids"].clone(), attention_mask=r["attention_mask"],
+                             uncond_attention_mask=r["attention_mask"], generator=torch.Generator().manual_seed(r["seed"]),
+                             text_vocab_len=tv, **r["kwargs"])
+        assert torch.equal(out, r["sampled"]) and torch.equal(ids, r["final_input_ids"]), r["name"]
+    for r in t["mmu"]:
+        if r["global_seed"] is not None:
+            torch.manual_seed(r["global_seed"])
+        assert torch.equal(G.mmu_generate(model, r["idx"], attention_mask=r["attention_mask"], **r["kwargs"]), r["out"]), r["name"]
+    for r in t["interleave"]:
+        torch.manual_seed(r["global_seed"])
+        img, txt = G.interleave_generate(model, r["input_ids"], r["uncond_input_ids"], soi_id=126085, eoi_id=126086, bos_id=126080,
+                                         mask_id=126336, num_vq_tokens=16, codebook_size=8192, max_seq_length=12, text_vocab_len=tv,
+                                         generator=torch.Generator().manual_seed(r["seed"]), **r["kwargs"])
+        assert torch.equal(img, r["image_ids"]) and torch.equal(txt, r["text_ids"]), r["name"]

@@ -17,26 +17,25 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-BASE = dict(pdl=0, gemm_splitk=1, gemm_l2pf=0, gemm_l2pf_mod=4, attn_split_tail=0)
+BASE = dict(pdl=0, gemm_splitk=1, gemm_l2pf=0, gemm_l2pf_mod=4, attn_split_tail=0, gemm_pair=0)
 VARIANTS = {
-    "base": {},
-    "splitk2": dict(gemm_splitk=2),
-    "splitk0": dict(gemm_splitk=0),
-    "attn_split": dict(attn_split_tail=1),
-    "pdl": dict(pdl=1),
-    "l2pf4": dict(gemm_l2pf=4),
+    "r1": {},                                                         # round-1 configuration
+    "cur": dict(pdl=1, gemm_splitk=2, attn_split_tail=1),             # current defaults
+    "cur_nopdl": dict(pdl=0, gemm_splitk=2, attn_split_tail=1),
+    "cur_sk1": dict(pdl=1, gemm_splitk=1, attn_split_tail=1),
+    "cur_sk0": dict(pdl=1, gemm_splitk=0, attn_split_tail=1),
+    "cur_noattn": dict(pdl=1, gemm_splitk=2, attn_split_tail=0),
+    "cur_pair": dict(pdl=1, gemm_splitk=2, attn_split_tail=1, gemm_pair=1),
+    "r1_pair": dict(gemm_pair=1),
     "l2pf8": dict(gemm_l2pf=8),
-    "l2pf16": dict(gemm_l2pf=16),
-    "l2pf8_all": dict(gemm_l2pf=8, gemm_l2pf_mod=1),
-    "all": dict(pdl=1, gemm_splitk=2, attn_split_tail=1),
-    "all_l2pf8": dict(pdl=1, gemm_splitk=2, attn_split_tail=1, gemm_l2pf=8),
 }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variants", nargs="*", default=list(VARIANTS))
-    ap.add_argument("--iters", type=int, default=6)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--rounds", type=int, default=4)
     ap.add_argument("--tiny", action="store_true")
     args = ap.parse_args()
     import bench
@@ -55,47 +54,59 @@ def main():
     def fwd():
         model.forward_rows(ids, rows_a=text_rows, out_a=out_a, rows_b=pos, col0_b=bench.TEXT_VOCAB, ncols_b=bench.CODEBOOK, out_b=out_b)
 
-    results, ref = [], None
+    import statistics
+    ref = None
+    acc = {name: dict(ms=[], gemm=[], attn=[], row=[]) for name in args.variants}
+    checks = {}
+    for rnd in range(args.rounds):  # alternate the variants: clock / temperature drift hits all of them alike
+        for name in args.variants:
+            opts = dict(BASE)
+            opts.update(VARIANTS[name])
+            for k, v in opts.items():
+                _lib.check(_lib.lib.mmdp_set_option(k.encode(), int(v)))
+            fwd()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+            acc[name]["ms"].append(e0.elapsed_time(e1) / args.iters)
+            _lib.lib.mmdp_prof_enable(1)
+            fwd()
+            prof = _lib.prof_summary()
+            _lib.lib.mmdp_prof_enable(0)
+            acc[name]["gemm"].append(prof["gemm"][0])
+            acc[name]["attn"].append(prof["attention"][0])
+            acc[name]["row"].append(prof["row"][0])
+            if rnd == 0:
+                a, b = out_a.float().clone(), out_b.float().clone()
+                rec = {"nan": bool(torch.isnan(a).any() or torch.isnan(b).any())}
+                if ref is None:
+                    ref = (a, b)
+                else:
+                    rec["max_abs_diff_text"] = float((a - ref[0]).abs().max())
+                    rec["max_abs_diff_img"] = float((b - ref[1]).abs().max())
+                    rec["mean_abs_diff_text"] = float((a - ref[0]).abs().mean())
+                    rec["frac_diff_text"] = float((a != ref[0]).float().mean())
+                    rec["logit_absmax"] = float(ref[0].abs().max())
+                fwd()
+                torch.cuda.synchronize()
+                rec["repeatable"] = bool(torch.equal(out_a.float(), a) and torch.equal(out_b.float(), b))
+                checks[name] = rec
+    results = []
+    flops = prof["gemm"][1]
     for name in args.variants:
-        opts = dict(BASE)
-        opts.update(VARIANTS[name])
-        for k, v in opts.items():
-            _lib.check(_lib.lib.mmdp_set_option(k.encode(), int(v)))
-        for _ in range(2):
-            fwd()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.iters):
-            fwd()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.iters
-        _lib.lib.mmdp_prof_enable(1)
-        fwd()
-        prof = _lib.prof_summary()
-        _lib.lib.mmdp_prof_enable(0)
-        a, b = out_a.float().clone(), out_b.float().clone()
-        rec = {"variant": name, "opts": opts, "ms_per_forward": ms, "gemm_ms": prof["gemm"][0], "attn_ms": prof["attention"][0],
-               "row_ms": prof["row"][0], "gemm_tflops": prof["gemm"][1] / prof["gemm"][0] / 1e9 if prof["gemm"][0] else None,
-               "attn_tflops": prof["attention"][1] / prof["attention"][0] / 1e9 if prof["attention"][0] else None,
-               "nan": bool(torch.isnan(a).any() or torch.isnan(b).any())}
-        if ref is None:
-            ref = (a, b)
-        else:
-            rec["max_abs_diff_text"] = float((a - ref[0]).abs().max())
-            rec["max_abs_diff_img"] = float((b - ref[1]).abs().max())
-            rec["frac_diff_text"] = float((a != ref[0]).float().mean())
-            rec["logit_absmax"] = float(ref[0].abs().max())
-        # repeatability of this variant
-        fwd()
-        torch.cuda.synchronize()
-        rec["repeatable"] = bool(torch.equal(out_a.float(), a) and torch.equal(out_b.float(), b))
+        m = acc[name]
+        rec = {"variant": name, "opts": {**BASE, **VARIANTS[name]}, "ms_per_forward_median": statistics.median(m["ms"]), "ms_per_forward_all": m["ms"],
+               "gemm_ms_median": statistics.median(m["gemm"]), "attn_ms_median": statistics.median(m["attn"]), "row_ms_median": statistics.median(m["row"]),
+               "gemm_tflops": flops / statistics.median(m["gemm"]) / 1e9, **checks[name]}
         results.append(rec)
         print(json.dumps(rec), flush=True)
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "sweep_forward.json"), "w") as f:
-            json.dump(results, f, indent=1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sweep_forward.json"), "w") as f:
+        json.dump(results, f, indent=1)
 
 
 if __name__ == "__main__":
