@@ -301,7 +301,7 @@ def workload_config(args, n_gpus):
                         "text_steps=128, cfg_img=4.0, cfg_scale=0, temperature=1.0, text_temperature=0 (BASELINE configs[1]"
                         + ("; TINY MODEL - plumbing check only, not a valid number" if args.tiny else "") + ")",
             "seq_len": 2414, "forwards_per_sample": 192,
-            "parallelism": (f"tensor-parallel x{n_gpus} (one prompt; heads/ff/vocab split, fp32 all-reduce over NCCL)" if getattr(args, "tp", False) and n_gpus > 1
+            "parallelism": (f"tensor-parallel x{n_gpus} (one prompt; heads/ff/vocab split, " + ("fused reduce+residual+norm+broadcast kernel over NVLink peer memory)" if getattr(args, "tp_collective", "p2p") == "p2p" else "fp32 all-reduce over NCCL)") if getattr(args, "tp", False) and n_gpus > 1
                             else f"replicas x{n_gpus} (independent prompts, no collective)"),
             "weights": "synthetic normal(0, 0.02) bf16, seeded", "l2": "16.2 GB of weights streamed per forward >> 126 MB L2 (no flush needed)"}
 
@@ -349,12 +349,12 @@ def build_model(model_cfg: dict, device: str, seed: int):
     return m
 
 
-def build_tp_model(model_cfg: dict, device: str, seed: int, rank: int, world: int):
+def build_tp_model(model_cfg: dict, device: str, seed: int, rank: int, world: int, collective: str = "p2p"):
     """Tensor-parallel model (BASELINE config 4): every rank materialises the same seeded tensors and keeps its shard."""
     from mmada_parallel_b200.tensor_parallel import TensorParallelLLaDA
     sd = dict(synthetic_tensors(model_cfg, device, seed))
     m = TensorParallelLLaDA(model_namespace(model_cfg), sd, rank, world, max_seq_len=model_cfg["max_sequence_length"], device=device,
-                            text_vocab_size=TEXT_VOCAB, codebook_size=CODEBOOK)
+                            text_vocab_size=TEXT_VOCAB, codebook_size=CODEBOOK, collective=collective)
     del sd
     torch.cuda.empty_cache()
     torch.cuda.synchronize()
@@ -565,8 +565,30 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
     del tp
     torch.cuda.empty_cache()
+    # the NCCL all-reduce formulation (round 1) on the same workload, one sample: what the peer-memory collective replaces
+    nccl_tok_s = None
+    try:
+        tpn = build_tp_model(model_cfg, device, 1000, rank, world, collective="nccl")
+        with torch.no_grad():
+            def st_n():
+                return DenoiseState(tpn, lay["input_ids"], uncon_text=lay["uncon_text"], uncon_image=lay["uncon_image"],
+                                    cfg_scale=GEN["cfg_scale"], cfg_img=GEN["cfg_img"], codebook_size=CODEBOOK, **pos_args)
+            dist.barrier()
+            torch.cuda.synchronize()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record()
+            denoise_loop(st_n(), generator=rng, **loop_kw)
+            n1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            nccl_tok_s = TOKENS_PER_SAMPLE / (max_over_ranks(n0.elapsed_time(n1), device=device) / 1e3)
+        del tpn
+        torch.cuda.empty_cache()
+    except Exception as e:
+        nccl_tok_s = f"error: {type(e).__name__}: {e}"[:200]
     v = steps * TOKENS_PER_SAMPLE / (ms / 1e3)
-    return {"metric": "denoised_tokens_per_sec", "value": v, "unit": "tokens/s", "n_gpus": world, "steps": steps, "scaling": "strong",
+    return {"metric": "denoised_tokens_per_sec", "value": v, "nccl_allreduce_baseline_tokens_per_s": nccl_tok_s,
+            "collective": "fused reduce + residual + RMSNorm + broadcast kernel over NVLink peer memory (csrc/tp_collective.cu)", "unit": "tokens/s", "n_gpus": world, "steps": steps, "scaling": "strong",
             "ms_per_step": ms / steps, "config": {"workload": "BASELINE configs[3]: ONE prompt, tensor-parallel attention/MLP/LM head over the GPUs",
                                                   "parallelism": f"tensor-parallel x{world}"},
             "tp_parity": {"logits_max_err_bf16_ulp_of_scale": max_ulp, "bound_ulp": 4.0, "ok": bool(max_ulp <= 4.0),
@@ -586,6 +608,8 @@ def main():
                     "baseline, VQ decode timing)")
     ap.add_argument("--variant", default="a", choices=["a", "m"], help="a = BASELINE configs[1] (the contract metric); m = extra line for "
                     "variant M (interleave_generate, CFG batch 2 every step, BASELINE configs[4] per GPU)")
+    ap.add_argument("--tp-collective", default="p2p", choices=["p2p", "nccl"], help="--tp: fused reduce + residual + norm + broadcast over "
+                    "NVLink peer memory (default) or the NCCL all-reduce baseline")
     ap.add_argument("--tp", action="store_true", help="N > 1: ONE sample tensor-parallel over the N GPUs (strong scaling, NCCL "
                     "all-reduce) instead of N independent replicas")
     args = ap.parse_args()
@@ -613,7 +637,7 @@ def main():
     model_cfg = MODEL_TINY if args.tiny else MODEL_8B
     tp_mode = args.tp and world > 1
     if tp_mode:
-        model = build_tp_model(model_cfg, device, 1000, rank, world)
+        model = build_tp_model(model_cfg, device, 1000, rank, world, collective=args.tp_collective)
         lay = synthetic_layout(seed=0)  # ONE prompt, all ranks work on it
     else:
         model = build_model(model_cfg, device, seed=1000)

@@ -67,6 +67,12 @@ SIGNATURES = {
     "mmdp_set_gemm_splitk": (None, [_i]),
     "mmdp_set_pdl": (None, [_i]),
     "mmdp_set_option": (_i, [C.c_char_p, _i]),
+    "mmdp_tp_alloc": (_i, [C.c_uint64, C.POINTER(_vp)]),
+    "mmdp_tp_free": (_i, [_vp]),
+    "mmdp_ipc_export": (_i, [_vp, _vp]),
+    "mmdp_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
+    "mmdp_ipc_close": (_i, [_vp]),
+    "mmdp_tp_reduce_norm": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _f, C.c_uint32, _vp, _vp]),
     "mmdp_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "mmdp_qkv_rope": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdp_qkv_rope_tp": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -164,6 +164,43 @@ MMDP_API int mmdp_lfq_decode(const int64_t* ids, float* zq, int B, int N, int bi
     return lfq_decode(ids, zq, B, N, bits, (cudaStream_t)stream);
 }
 
+// ---- tensor-parallel plumbing: device buffers shared between the ranks of one node through CUDA IPC ------------------------
+MMDP_API int mmdp_tp_alloc(uint64_t bytes, void** out) {
+    if (!out || bytes == 0) return set_error("mmdp_tp_alloc: bad arguments");
+    MMDP_CUDA(cudaMalloc(out, bytes));
+    MMDP_CUDA(cudaMemset(*out, 0, bytes));
+    return 0;
+}
+MMDP_API int mmdp_tp_free(void* p) {
+    if (p) MMDP_CUDA(cudaFree(p));
+    return 0;
+}
+MMDP_API int mmdp_ipc_export(void* p, uint8_t* handle64) {
+    if (!p || !handle64) return set_error("mmdp_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    MMDP_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+MMDP_API int mmdp_ipc_import(const uint8_t* handle64, void** out) {
+    if (!handle64 || !out) return set_error("mmdp_ipc_import: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    MMDP_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));  // maps the peer's buffer; enables P2P access
+    return 0;
+}
+MMDP_API int mmdp_ipc_close(void* p) {
+    if (p) MMDP_CUDA(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+MMDP_API int mmdp_tp_reduce_norm(const float* const* part, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks,
+                        int my_rank, uint16_t* x_shard, const uint16_t* weight, int row0, int nrows, int d, float eps,
+                        uint32_t epoch, uint32_t* done_counter, void* stream) {
+    return tp_reduce_norm(part, n_src, xn, flags, n_ranks, my_rank, x_shard, weight, row0, nrows, d, eps, epoch, done_counter,
+                          (cudaStream_t)stream);
+}
+
 MMDP_API void mmdp_prof_enable(int on) { prof_enable(on); }
 MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches) { return prof_summary(ms, work, launches); }
 MMDP_API long long mmdp_launch_count(int reset) { return launch_count(reset); }

@@ -146,5 +146,9 @@ int image_step_t2i(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64
                    int64_t* ids, const int* pos, int64_t mask_id, int64_t vq_offset, int32_t* sampled_ws, float* selp_ws,
                    uint8_t* unknown_ws, uint8_t* masking_out, cudaStream_t stream);
 int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream_t stream);
+// tensor-parallel collective over NVLink peer memory (tp_collective.cu)
+int tp_reduce_norm(const float* const* part, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks, int my_rank,
+                   uint16_t* x_shard, const uint16_t* w, int row0, int nrows, int d, float eps, uint32_t epoch,
+                   unsigned int* done_counter, cudaStream_t stream);
 
 }  // namespace mmdp

@@ -3,19 +3,25 @@ GPUs of one node. The reference has no tensor parallelism; this f
 
   * attention: heads split (q/k/v_proj column-parallel, attn_out row-parallel); MLP: ff split (ff_proj/up_proj
     column-parallel, ff_out row-parallel); LM head: vocabulary rows split (and the VQ-codebook window split separately);
-  * the two row-parallel GEMMs per layer produce fp32 PARTIAL sums (MMDP_EPI_F32) that are all-reduced in fp32 over
-    NCCL/NVLink and only then rounded to bf16 and added to the residual (mmdp_resid_add_f32), i.e. the same rounding
-    points as the single-GPU epilogue `bf16(bf16(acc) + x)` - a bf16 all-reduce would round twice;
-  * every rank then holds the full residual stream, gathers the logits slices it needs (all_gather) and runs the SAME
-    sampling kernels on the same noise (identical generator seeds), so the id sequence stays in sync without broadcasts.
+  * the two row-parallel GEMMs per layer produce fp32 PARTIAL sums (MMDP_EPI_F32). What follows them - the cross-rank sum,
+    the residual add, the NEXT RMSNorm and the distribution of its output to all ranks - is one kernel per rank over NVLink
+    peer memory (`mmdp_tp_reduce_norm`, csrc/tp_collective.cu): every rank reduces the rows it owns in fixed rank order,
+    applies the single-GPU rounding points `x = bf16(bf16(sum) + x)` and the norm, and stores the bf16 result into every
+    rank's activation buffer. The residual stream is therefore row-sharded (M / TP rows per rank), the normalised activations
+    are replicated; 0.75x the bytes of an fp32 all-reduce and no separate residual / RMSNorm launches;
+  * every rank gathers the logits slices it needs (NCCL all_gather, once per forward) and runs the SAME sampling kernels on
+    the same noise (identical generator seeds), so the id sequence stays in sync without broadcasts.
 
-The layer loop lives here (Python calling the C-ABI ops of libmmdp.so); the collective is torch.distributed (NCCL).
-Fusing the all-reduce into the GEMM epilogue over NVLink peer memory is the planned next step.
+`collective="nccl"` keeps round 1's formulation (fp32 `dist.all_reduce` + `mmdp_resid_add_f32` + `mmdp_rmsnorm` between the
+kernels) as the measured baseline of the peer-memory path (bench.py --tp --tp-collective nccl).
+Buffers shared between the ranks are plain cudaMalloc allocations exported with CUDA IPC (`mmdp_ipc_export/import`); the
+handles travel through `dist.all_gather_object`.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
-from typing import Dict, Optional
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -59,15 +65,66 @@ def shard_state_dict(sd: Dict[str, torch.Tensor], n_layers: int, n_heads: int, r
     return out
 
 
+def row_partition(M: int, tp: int, rank: int):
+    """Rows of the residual stream rank `rank` owns: the balanced split [rank * M // tp, (rank + 1) * M // tp) - every
+    rank owns at least one row when M >= tp."""
+    r0 = rank * M // tp
+    return r0, (rank + 1) * M // tp - r0
+
+
+class _DeviceArray:
+    """Zero-copy torch view of a raw device allocation (a cudaMalloc made by libmmdp for IPC export)."""
+
+    def __init__(self, ptr_value: int, numel: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (int(ptr_value), False), "version": 3}
+
+
+class _SharedBuffer:
+    """One buffer per rank, visible to all ranks of the node: `ptrs[r]` is rank r's allocation mapped into this process."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, group):
+        self.rank, self.world = rank, world
+        own = C.c_void_p()
+        check(lib.mmdp_tp_alloc(nbytes, C.byref(own)))
+        self.own = own.value
+        handle = (C.c_uint8 * 64)()
+        check(lib.mmdp_ipc_export(self.own, handle))
+        handles: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs: List[int] = []
+        self._imported: List[int] = []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self.own)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+            check(lib.mmdp_ipc_import(buf, C.byref(p)))
+            self.ptrs.append(p.value)
+            self._imported.append(p.value)
+        self.array = (C.c_void_p * world)(*self.ptrs)   # host array of device pointers for the C ABI
+
+    def close(self):
+        for p in self._imported:
+            lib.mmdp_ipc_close(p)
+        self._imported = []
+        if self.own:
+            lib.mmdp_tp_free(self.own)
+            self.own = None
+
+
 class TensorParallelLLaDA:
     """Same call contract as model.LLaDAForMultiModalGeneration (`forward_rows`, `__call__`), one rank of a TP group."""
 
     def __init__(self, config, state_dict: Dict[str, torch.Tensor], tp_rank: int, tp_size: int, group=None,
                  max_seq_len: Optional[int] = None, max_batch: int = 1, device: str = "cuda:0", text_vocab_size: int = 126356,
-                 codebook_size: int = 8192):
+                 codebook_size: int = 8192, collective: str = "p2p"):
         if not torch.cuda.is_available():
             raise _lib.MmdpError("mmada_parallel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if collective not in ("p2p", "nccl"):
+            raise ValueError("collective must be 'p2p' (NVLink peer-memory kernel) or 'nccl' (all-reduce baseline)")
         self.config, self.group, self.rank, self.tp = config, group, tp_rank, tp_size
+        self.collective = collective if tp_size > 1 else "nccl"
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         g = lambda k, dflt=None: getattr(config, k, dflt)
@@ -90,15 +147,37 @@ class TensorParallelLLaDA:
         cos, sin = rope_tables(128, float(g("rope_theta", 10000.0)), self.max_seq_len)
         self.cos, self.sin = cos.to(self.device), sin.to(self.device)
         M, d, bf = self.max_batch * self.max_seq_len, self.d_model, dict(dtype=torch.bfloat16, device=self.device)
-        self.x = torch.empty((M, d), **bf)
-        self.xn = torch.empty((M, d), **bf)
+        self.Mmax = M
         self.q = torch.empty((M, self.d_attn), **bf)
         self.k = torch.empty((M, self.d_attn), **bf)
         self.att = torch.empty((M, self.d_attn), **bf)
         self.h = torch.empty((M, self.ff_local), **bf)
-        self.part = torch.empty((M, d), dtype=torch.float32, device=self.device)
         self.vt = None
         self._vt_key = None
+        if self.collective == "p2p":
+            if M < tp_size:
+                raise ValueError("the workspace must hold at least one row per rank")
+            self._part = [_SharedBuffer(M * d * 4, tp_rank, tp_size, group) for _ in range(2)]   # used alternately
+            self._xn = _SharedBuffer(M * d * 2, tp_rank, tp_size, group)
+            self._flags = _SharedBuffer(2 * 8 * 4, tp_rank, tp_size, group)
+            self.xn = torch.as_tensor(_DeviceArray(self._xn.own, M * d, "<u2"), device=self.device).view(torch.bfloat16).view(M, d)
+            self.x = torch.empty(((M + tp_size - 1) // tp_size + 1, d), **bf)                    # this rank's rows of the residual stream
+            self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._epoch = 0
+            torch.cuda.synchronize()
+            dist.barrier(group=group)  # every rank has mapped every buffer before the first peer access
+        else:
+            self.x = torch.empty((M, d), **bf)
+            self.xn = torch.empty((M, d), **bf)
+            self.part = torch.empty((M, d), dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        for b in getattr(self, "_part", []) + [getattr(self, "_xn", None), getattr(self, "_flags", None)]:
+            if b is not None:
+                try:
+                    b.close()
+                except Exception:
+                    pass
 
     def eval(self):
         return self
@@ -117,57 +196,97 @@ class TensorParallelLLaDA:
         dist.all_gather_into_tensor(buf, local.contiguous(), group=self.group)
         out.view(n, self.tp, c).copy_(buf.permute(1, 0, 2))
 
-    def _hidden(self, ids: torch.Tensor):
-        B, L = ids.shape
-        M, d, s = B * L, self.d_model, stream_ptr()
-        if M > self.x.shape[0]:
-            raise _lib.MmdpError("TensorParallelLLaDA: batch x length exceeds the workspace")
-        Lpad = (L + 7) // 8 * 8
-        if self._vt_key != (B, Lpad):
-            self.vt = torch.zeros((B, self.h_local, 128, Lpad), dtype=torch.bfloat16, device=self.device)
-            self._vt_key = (B, Lpad)
-        x, xn, part, w = self.x[:M], self.xn[:M], self.part[:M], self.w
-        check(lib.mmdp_embed(ptr(ids), ptr(w["wte"]), ptr(x), M, d, w["wte"].shape[0], s))
+    # ------------------------------------------------------------------------------------------------------------------
+    def _reduce_norm(self, part_idx: Optional[int], weight: torch.Tensor, M: int):
+        """Cross-rank sum of the fp32 partials (part_idx None: no partials), residual add on this rank's rows, RMSNorm with
+        `weight`, result into every rank's xn; on return (in stream order) all M rows of self.xn are valid."""
+        self._epoch += 1
+        r0, nrows = row_partition(M, self.tp, self.rank)
+        part = self._part[part_idx].array if part_idx is not None else None
+        check(lib.mmdp_tp_reduce_norm(part, self.tp if part_idx is not None else 0, self._xn.array, self._flags.array, self.tp, self.rank,
+                                      ptr(self.x), ptr(weight), r0, nrows, self.d_model, self.rms_eps, self._epoch, ptr(self._done),
+                                      stream_ptr()))
+
+    def _layers(self, B: int, L: int, M: int, Lpad: int):
+        d, s, w = self.d_model, stream_ptr(), self.w
         scale = 1.0 / math.sqrt(128.0)
+        p2p = self.collective == "p2p"
+        x, xn = self.x, self.xn
         for i in range(self.n_layers):
             p = f"blocks.{i}."
-            check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "attn_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
+            if not p2p:
+                check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "attn_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
             check(lib.mmdp_qkv_rope_tp(ptr(xn), d, ptr(w[p + "wqkv"]), M, d, self.h_local, L, Lpad, ptr(self.cos), ptr(self.sin),
                                        ptr(self.q), ptr(self.k), ptr(self.vt), s))
             check(lib.mmdp_attention(ptr(self.q), ptr(self.k), ptr(self.vt), ptr(self.att), B, self.h_local, L, Lpad, scale, s))
+            part = self._part[0].own if p2p else ptr(self.part)
             check(lib.mmdp_gemm_bf16(EPI_F32, ptr(self.att), self.d_attn, ptr(w[p + "wo"]), self.d_attn, M, d, self.d_attn,
-                                     ptr(part), d, None, 0, s))
-            self._allreduce(part)
-            check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(part), d, M, d, s))
-            check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "ff_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
+                                     part, d, None, 0, s))
+            if p2p:
+                self._reduce_norm(0, w[p + "ff_norm"], M)
+            else:
+                self._allreduce(self.part[:M])
+                check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(self.part), d, M, d, s))
+                check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "ff_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
             check(lib.mmdp_gemm_bf16(EPI_SWIGLU, ptr(xn), d, ptr(w[p + "w13"]), d, M, 2 * self.ff_local, d, ptr(self.h),
                                      self.ff_local, None, 0, s))
+            part = self._part[1].own if p2p else ptr(self.part)
             check(lib.mmdp_gemm_bf16(EPI_F32, ptr(self.h), self.ff_local, ptr(w[p + "w2"]), self.ff_local, M, d, self.ff_local,
-                                     ptr(part), d, None, 0, s))
-            self._allreduce(part)
-            check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(part), d, M, d, s))
-        return x
+                                     part, d, None, 0, s))
+            if p2p:
+                nxt = w[f"blocks.{i + 1}.attn_norm"] if i + 1 < self.n_layers else w["ln_f"]
+                self._reduce_norm(1, nxt, M)
+            else:
+                self._allreduce(self.part[:M])
+                check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(self.part), d, M, d, s))
+
+    def _final_norm(self, ids: torch.Tensor) -> torch.Tensor:
+        """Runs embedding + all blocks; returns ln_f(x) for ALL rows [M, d] (p2p) or the raw residual stream x (nccl)."""
+        B, L = ids.shape
+        M, d, s = B * L, self.d_model, stream_ptr()
+        if M > self.Mmax:
+            raise _lib.MmdpError("TensorParallelLLaDA: batch x length exceeds the workspace")
+        Lpad = (L + 7) // 8 * 8
+        if self._vt_key != (B, Lpad, L):
+            self.vt = torch.zeros((B, self.h_local, 128, Lpad), dtype=torch.bfloat16, device=self.device)
+            self._vt_key = (B, Lpad, L)
+        wte = self.w["wte"]
+        if self.collective == "p2p":
+            if M < self.tp:
+                raise _lib.MmdpError("TensorParallelLLaDA: needs at least one token per rank")
+            r0, nrows = row_partition(M, self.tp, self.rank)
+            check(lib.mmdp_embed(ids.data_ptr() + r0 * 8, ptr(wte), ptr(self.x), nrows, d, wte.shape[0], s))   # this rank's rows only
+            self._reduce_norm(None, self.w["blocks.0.attn_norm"], M)
+        else:
+            check(lib.mmdp_embed(ptr(ids), ptr(wte), ptr(self.x), M, d, wte.shape[0], s))
+        self._layers(B, L, M, Lpad)
+        return self.xn if self.collective == "p2p" else self.x
 
     @torch.no_grad()
     def forward_rows(self, ids: torch.Tensor, rows_a: Optional[torch.Tensor] = None, rows_b: Optional[torch.Tensor] = None,
                      col0_b: int = 0, ncols_b: int = 0, out_a: Optional[torch.Tensor] = None, out_b: Optional[torch.Tensor] = None):
-        x = self._hidden(ids.contiguous())
+        hid = self._final_norm(ids.contiguous())
         d, s, w = self.d_model, stream_ptr(), self.w
+
+        def rows_normed(rows):
+            n = rows.numel()
+            if self.collective == "p2p":
+                return hid.index_select(0, rows.long())                    # already ln_f(x): the last collective used ln_f's weight
+            xr = torch.empty((n, d), dtype=torch.bfloat16, device=self.device)
+            check(lib.mmdp_rmsnorm(ptr(hid), d, ptr(rows), ptr(w["ln_f"]), ptr(xr), d, n, d, self.rms_eps, s))
+            return xr
+
         ra = rb = None
         if rows_a is not None and rows_a.numel():
             n = rows_a.numel()
-            xr = torch.empty((n, d), dtype=torch.bfloat16, device=self.device)
-            check(lib.mmdp_rmsnorm(ptr(x), d, ptr(rows_a), ptr(w["ln_f"]), ptr(xr), d, n, d, self.rms_eps, s))
-            loc = _lib.gemm_bf16(xr, w["head"], EPI_PLAIN)
+            loc = _lib.gemm_bf16(rows_normed(rows_a), w["head"], EPI_PLAIN)
             ra = out_a if out_a is not None else torch.empty((n, self.vocab_rows), dtype=torch.bfloat16, device=self.device)
             self._gather_cols(loc, ra)
         if rows_b is not None and rows_b.numel():
             if col0_b != self.vq_col0 or ncols_b != self.vq_cols:
                 raise _lib.MmdpError("TensorParallelLLaDA: the column window must be the VQ codebook window given at construction")
             n = rows_b.numel()
-            xr = torch.empty((n, d), dtype=torch.bfloat16, device=self.device)
-            check(lib.mmdp_rmsnorm(ptr(x), d, ptr(rows_b), ptr(w["ln_f"]), ptr(xr), d, n, d, self.rms_eps, s))
-            loc = _lib.gemm_bf16(xr, w["head_vq"], EPI_PLAIN)
+            loc = _lib.gemm_bf16(rows_normed(rows_b), w["head_vq"], EPI_PLAIN)
             rb = out_b if out_b is not None else torch.empty((n, ncols_b), dtype=torch.bfloat16, device=self.device)
             self._gather_cols(loc, rb)
         return ra, rb

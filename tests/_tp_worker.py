@@ -25,11 +25,28 @@ from mmada_parallel_b200.tensor_parallel import TensorParallelLLaDA  # noqa: E40
 cfg = llada.make_config(d_model=512, n_heads=4, n_layers=2, mlp_hidden_size=1024, vocab_size=134656,
                         max_sequence_length=512)
 sd = llada.make_weights(cfg, seed=77)
-tp = TensorParallelLLaDA(cfg, sd, rank, world, max_seq_len=512, device=f"cuda:{rank}")
+tp = TensorParallelLLaDA(cfg, sd, rank, world, max_seq_len=512, device=f"cuda:{rank}")              # NVLink peer-memory collective
+tp_nccl = TensorParallelLLaDA(cfg, sd, rank, world, max_seq_len=512, device=f"cuda:{rank}", collective="nccl")
 lay = layout_a()
 ids = lay["input_ids"].cuda()
 lg_tp = tp(ids).logits
+lg_nccl = tp_nccl(ids).logits
 ok = True
+# same rounding points, different fp32 summation order across ranks (fixed rank order vs NCCL's): inside the 4-ulp bound, and
+# the peer-memory path is bitwise repeatable
+d_modes = (lg_tp.float() - lg_nccl.float()).abs().max().item()
+rep = torch.equal(tp(ids).logits, lg_tp)
+g = [None] * world
+dist.all_gather_object(g, (d_modes, rep, float(lg_tp.float().abs().max())))
+if rank == 0:
+    print("p2p vs nccl collective: max |dlogit| per rank", [round(x[0], 4) for x in g], "repeatable", [x[1] for x in g])
+    ok = ok and all(x[1] for x in g) and all(x[0] <= 4 * x[2] * 2.0 ** -8 for x in g)
+# every rank holds identical logits (the activations are broadcast, the head slices all-gathered)
+ref = lg_tp.clone()
+dist.broadcast(ref, src=0)
+same_logits = torch.tensor([1 if torch.equal(ref, lg_tp) else 0], device=f"cuda:{rank}")
+dist.all_reduce(same_logits, op=dist.ReduceOp.MIN)
+ok = ok and int(same_logits.item()) == 1
 if rank == 0:
     single = LLaDAForMultiModalGeneration(cfg, max_seq_len=512, max_batch=1, device="cuda:0")
     single.load_state_dict(sd)

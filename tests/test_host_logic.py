@@ -159,3 +159,17 @@ def test_preview_host_helpers_match_oracle():
         decode_vq_to_image(ids, None, None, 32, 32, None)
     with pytest.raises(TypeError):
         decode_vq_to_image(ids, None, None, 32, 32, object())
+
+
+def test_tensor_parallel_row_partition():
+    """Rows of the residual stream owned per rank (tensor_parallel.row_partition): disjoint, in order, covering [0, M), and
+    at least one row per rank whenever M >= tp (the peer-memory collective needs every rank to signal)."""
+    from mmada_parallel_b200.tensor_parallel import row_partition
+    for M in (8, 9, 77, 2414, 4682, 4096):
+        for tp in (1, 2, 4, 8):
+            parts = [row_partition(M, tp, r) for r in range(tp)]
+            assert parts[0][0] == 0 and sum(n for _, n in parts) == M
+            for (a0, an), (b0, _) in zip(parts, parts[1:]):
+                assert a0 + an == b0
+            assert all(n >= 1 for _, n in parts)
+            assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
