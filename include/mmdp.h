@@ -41,9 +41,9 @@ MMDP_API const char* mmdp_last_error(void);
 MMDP_API void mmdp_prof_enable(int on);
 MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches);
 MMDP_API long long mmdp_launch_count(int reset);
-/* Kernel selection for large GEMMs: 0 = one CTA per 128xN tile (cta_group::1), 1 = CTA pair per 256xN tile (cta_group::2).
- * 2 = pair kernel only for M >= 4096 and N >= 8192. Results are bit-identical (same K order); also settable with the
- * environment variable MMDP_GEMM_PAIR. */
+/* Kernel selection for GEMMs with M > 256: 1 (default) = CTA pair per 256xN tile (cta_group::2), 0 = one CTA per 128xN tile
+ * (cta_group::1, with its split-K tail), 2 = pair kernel only for M >= 4096 and N >= 8192. Without the split-K tail the two
+ * kernels are bit-identical (same K order); also settable with the environment variable MMDP_GEMM_PAIR. */
 MMDP_API void mmdp_set_gemm_pair(int on);
 /* Attention kernel generation (csrc/attention_dispatch.cu): 6 = O and P in tensor memory, 64-wide KV blocks (default);
  * 5 = same with 128-wide KV blocks; 3 = O in registers, P through shared memory. Also MMDP_ATTN=3|5|6. Same results up to

@@ -348,8 +348,11 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
         default:
             return set_error("gemm: unknown epilogue");
     }
-    // kernel selection: MMDP_GEMM_PAIR=1 routes large problems to the CTA-pair (cta_group::2) kernel of gemm2.cu
-    // mode 2 (auto): only where the pair kernel measured faster - many-row problems with wide N (M pads to 256-row tiles)
+    // kernel selection. Default (MMDP_GEMM_PAIR=1): problems with more than two m-tiles go to the CTA-pair (cta_group::2)
+    // kernel of gemm2.cu, whose 256 x BN tiles read a third less operand data per SM and flop - measured on the four body
+    // GEMMs of the bench workload (M = 2414): QKV +8.5 %, gate/up +5.7 %, attn_out +9 %, ff_out +1.6 %, one forward -3.8 %
+    // (profiles/r02). Small-M problems (the restricted LM head on 256 text rows) stay on the 1-CTA kernel below with its
+    // split-K tail. 0 = always 1-CTA, 2 = pair only for M >= 4096 and N >= 8192.
     const int pm = gemm_pair_mode();
     if ((pm == 1 && M > 256) || (pm == 2 && M >= 4096 && N >= 8192)) return gemm_bf16_pair(epi, A, lda, W, ldw, M, N, K, C, ldc, resid, ldr, qa, stream);
     GemmParams p{};

@@ -116,6 +116,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above overlaps the tail of the previous kernel in the stream (programmatic dependent launch)
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int num_m = (p.M + 2 * P_BM - 1) / (2 * P_BM);  // pair tiles along M
     const int num_n = (p.N + BN - 1) / BN;
@@ -207,17 +210,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int EPI, int BN>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;  // bit per device
+    int dev = 0;
+    MMDP_CUDA(cudaGetDevice(&dev));
+    if (!(attr_set >> (dev & 63) & 1ull)) {
         MMDP_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<BN>::kSmem));
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     const int num_tiles = ((p.M + 2 * P_BM - 1) / (2 * P_BM)) * ((p.N + BN - 1) / BN);
     const int pairs = num_sms() / 2;
     const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
     LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    gemm_pair_kernel<EPI, BN><<<grid, kPairThreads, PairCfg<BN>::kSmem, stream>>>(tmA, tmB, p);
-    MMDP_CUDA(cudaGetLastError());
+    MMDP_CUDA(launch_ex(gemm_pair_kernel<EPI, BN>, dim3(grid), dim3(kPairThreads), PairCfg<BN>::kSmem, stream, pdl_mode() != 0, false, tmA, tmB, p));
     return 0;
 }
 

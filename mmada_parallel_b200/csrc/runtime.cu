@@ -47,7 +47,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"gemm_splitk", "MMDP_GEMM_SPLITK", 2, 0, false},
     {"gemm_l2pf", "MMDP_GEMM_L2PF", 0, 0, false},
     {"gemm_l2pf_mod", "MMDP_GEMM_L2PF_MOD", 4, 0, false},
-    {"gemm_pair", "MMDP_GEMM_PAIR", 0, 0, false},
+    {"gemm_pair", "MMDP_GEMM_PAIR", 1, 0, false},
     {"gemm_group_m", "MMDP_GEMM_GROUP_M", -1, 0, false},
     {"attn_split_tail", "MMDP_ATTN_SPLIT_TAIL", 1, 0, false},
     {"attn_poly", "MMDP_ATTN_POLY", 4, 0, false},

@@ -142,9 +142,22 @@ __global__ void __launch_bounds__(kThreads) text_rows_kernel(TextRowArgs a) {
         if (s_best[i] > best || (s_best[i] == best && s_idx[i] < best_i)) { best = s_best[i]; best_i = s_idx[i]; best_logit = s_bl[i]; }
     }
 
-    // pass 2 (row now L2-resident): sum exp(l - max) in fp64 == F.softmax(logits.to(float64)) denominator
-    double sum = 0.0;
+    // pass 2 (row now L2-resident): sum exp(l - max) in fp64 == F.softmax(logits.to(float64)) denominator.
+    // A bf16 logit takes few distinct values: exp(double(v) - max) is tabulated once per row for every bf16 pattern with
+    // 2^-6 <= |v| < 2^6 (2 signs x 12 exponents x 128 mantissas = 24 KB of shared memory, 6 fp64 exp per thread) and the pass
+    // becomes a table gather + fp64 add - the ~0.5 % of the elements outside the window take the direct exp. The terms are
+    // bit-identical to the direct evaluation (same expression), only their summation order is the kernel's own.
+    constexpr int kTabExp0 = 121, kTabExps = 12;                 // biased bf16 exponents [121, 133)
+    __shared__ double s_tab[2 * kTabExps * 128];
     const double dmx = (double)mx;
+    for (int t = threadIdx.x; t < 2 * kTabExps * 128; t += kThreads) {
+        const uint32_t sgn = t / (kTabExps * 128), rem = t - sgn * (kTabExps * 128);
+        const uint32_t bits = (sgn << 15) | ((kTabExp0 + rem / 128) << 7) | (rem & 127);
+        const double d = (double)__uint_as_float(bits << 16) - dmx;
+        s_tab[t] = d > -64.0 ? exp(d) : 0.0;                    // exp(-64) < 2^-92: below half an ulp of any fp64 sum >= 1
+    }
+    __syncthreads();
+    double sum = 0.0;
     for (int i = threadIdx.x; i < nvec; i += kThreads) {
         float c[8], u[8];
         unpack8(c4[i], c);
@@ -152,8 +165,14 @@ __global__ void __launch_bounds__(kThreads) text_rows_kernel(TextRowArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float l = text_logit(c[j], has_u ? u[j] : 0.f, a.cfg, has_u);
-            const double d = (double)l - dmx;
-            if (d > -64.0) sum += exp(d);  // exp(-64) < 2^-92: below half an ulp of any fp64 sum >= 1
+            const uint32_t b = __float_as_uint(l) >> 16;
+            const uint32_t e = ((b >> 7) & 0xffu) - kTabExp0;
+            if (e < (uint32_t)kTabExps) {
+                sum += s_tab[((b >> 15) * kTabExps + e) * 128 + (b & 127u)];
+            } else {
+                const double d = (double)l - dmx;
+                if (d > -64.0) sum += exp(d);
+            }
         }
     }
 #pragma unroll

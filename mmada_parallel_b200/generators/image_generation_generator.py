@@ -126,7 +126,8 @@ def generate_image(
                                       float(temperature), ptr(u2), float(temperature), keep_n, ptr(x), ptr(rows), int(mask_token_id),
                                       off, ptr(sampled_ws), ptr(selp_ws), ptr(unk_ws), None, stream_ptr()))
         if _trace is not None:
-            _trace.append(dict(step=step, keep_n=keep_n, sampled=sampled_ws[:n].long().clone(), x=x[0].clone()))
+            # (the reference clamps keep_n to n - 1 IN PLACE inside mask_by_random_topk, generation_utils.py:57; the kernel clamps too)
+            _trace.append(dict(step=step, keep_n=min(keep_n, n - 1), sampled=sampled_ws[:n].long().clone(), x=x[0].clone()))
         if debug and debug_log_dir:
             import numpy as np
             base = os.path.join(debug_log_dir, f"step_{step}")
