@@ -47,6 +47,7 @@ def test_gemm_grouped_tile_order(M):
     residual epilogues (the latter with its split-K tail) against the fp32 reference, and bit-identical to the plain order."""
     import os
     from mmada_parallel_b200 import _lib
+    _lib.lib.mmdp_set_gemm_pair(0)
     torch.manual_seed(M)
     K, N = 512, 1024
     a = bf(torch.randn(M, K, device="cuda") * 0.5)
@@ -57,6 +58,7 @@ def test_gemm_grouped_tile_order(M):
     assert_ulp(got, lin, 1, f"grouped gemm {M}")
     assert_ulp(_lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r), bf(lin.float() + r.float()), 2, f"grouped resid {M}", mag=lin)
     assert torch.equal(got, _lib.gemm_bf16(a, w)), "repeatable"
+    _lib.lib.mmdp_set_gemm_pair(1)
 
 
 def test_gemm_strided_views():
@@ -293,6 +295,7 @@ def test_gemm_splitk_tail_matches_unsplit(epi):
     torch.manual_seed(12)
     fn = run()
     try:
+        _lib.lib.mmdp_set_gemm_pair(0)  # the 1-CTA kernel (default for M <= 256; the pair kernel has no split-K tail)
         _lib.lib.mmdp_set_gemm_splitk(0)
         ref = fn()
         _lib.lib.mmdp_set_gemm_splitk(3)  # split whenever a partial last wave exists
@@ -300,8 +303,34 @@ def test_gemm_splitk_tail_matches_unsplit(epi):
         again = fn()
     finally:
         _lib.lib.mmdp_set_gemm_splitk(2)
+        _lib.lib.mmdp_set_gemm_pair(1)
     assert torch.equal(got, again), "split-K tail must be deterministic"
     diff = (got - ref).abs()
     scale = ref.abs().max().item()
     assert diff.max().item() <= 2 * scale * 2.0 ** -8, (epi, diff.max().item())
     assert (got != ref).float().mean().item() < 0.02, (epi, (got != ref).float().mean().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 1000, 520), (2414, 4096, 1024), (300, 512, 768)])
+def test_gemm_pair_kernel_bit_identical_to_single(M, N, K):
+    """The CTA-pair (cta_group::2) kernel - the default for M > 256 - accumulates K in the same order as the 1-CTA kernel
+    without its split-K tail: plain, residual and SwiGLU epilogues must agree bit for bit."""
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(M + K)
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    w = bf(torch.randn(N, K, device="cuda") * 0.05)
+    r = bf(torch.randn(M, N, device="cuda"))
+    cases = [(_lib.EPI_PLAIN, {}), (_lib.EPI_RESID, dict(resid=r))]
+    if N % 256 == 0:
+        cases.append((_lib.EPI_SWIGLU, {}))
+    try:
+        _lib.lib.mmdp_set_gemm_splitk(0)
+        for epi, kw in cases:
+            _lib.lib.mmdp_set_gemm_pair(0)
+            ref = _lib.gemm_bf16(a, w, epi, **kw)
+            _lib.lib.mmdp_set_gemm_pair(1)
+            got = _lib.gemm_bf16(a, w, epi, **kw)
+            assert torch.equal(got, ref), epi
+    finally:
+        _lib.lib.mmdp_set_gemm_splitk(2)
+        _lib.lib.mmdp_set_gemm_pair(1)
