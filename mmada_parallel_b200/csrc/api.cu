@@ -194,11 +194,20 @@ MMDP_API int mmdp_ipc_close(void* p) {
     if (p) MMDP_CUDA(cudaIpcCloseMemHandle(p));
     return 0;
 }
-MMDP_API int mmdp_tp_reduce_norm(const float* const* part, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks,
-                        int my_rank, uint16_t* x_shard, const uint16_t* weight, int row0, int nrows, int d, float eps,
+MMDP_API int mmdp_tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16_t* const* xn, uint32_t* const* flags,
+                        int n_ranks, int my_rank, uint16_t* x_shard, const uint16_t* weight, int row0, int nrows, int d, float eps,
                         uint32_t epoch, uint32_t* done_counter, void* stream) {
-    return tp_reduce_norm(part, n_src, xn, flags, n_ranks, my_rank, x_shard, weight, row0, nrows, d, eps, epoch, done_counter,
-                          (cudaStream_t)stream);
+    return tp_reduce_norm(recv_local, rows_per_rank, n_src, xn, flags, n_ranks, my_rank, x_shard, weight, row0, nrows, d, eps, epoch,
+                          done_counter, (cudaStream_t)stream);
+}
+MMDP_API int mmdp_gemm_f32_scatter(const uint16_t* A, int lda, const uint16_t* W, int ldw, int M, int N, int K, float* const* recv,
+                          int n_ranks, int rows_per_rank, int slot, void* stream) {
+    if (!recv || n_ranks < 1 || n_ranks > 8) return set_error("mmdp_gemm_f32_scatter: bad rank layout");
+    if (rows_per_rank <= 0 || (M + rows_per_rank - 1) / rows_per_rank > n_ranks) return set_error("mmdp_gemm_f32_scatter: M does not fit n_ranks x rows_per_rank");
+    GemmScatter sc{};
+    for (int r = 0; r < n_ranks; ++r) sc.dst[r] = recv[r];
+    sc.rows_per_rank = rows_per_rank; sc.slot = slot;
+    return gemm_bf16(EPI_F32, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, nullptr, N, nullptr, 0, nullptr, (cudaStream_t)stream, &sc);
 }
 
 MMDP_API void mmdp_prof_enable(int on) { prof_enable(on); }

@@ -254,27 +254,44 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W,
                                                         const double* __restrict__ stats, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int swish, int compact) {
-    const int b = blockIdx.y, Wp = W + 2, Hp = H + 2, cpg = C / 32;
-    const long long n = (long long)Hp * Wp * C;
-    const double cnt = (double)H * W * cpg;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % C);
-        const long long pix = i / C;
-        const int yy = (int)(pix / Wp), xx = (int)(pix - (long long)yy * Wp);
-        const bool interior = yy >= 1 && yy <= H && xx >= 1 && xx <= W;
-        const size_t src = (size_t)b * n + i;
+    // one CTA per (padded image row, batch image): float4 over the channels, the 32 group means / inverse deviations are
+    // evaluated once per CTA (fp64, like the sums they come from), no per-element 64-bit division
+    const int b = blockIdx.y, yy = blockIdx.x, Wp = W + 2, Hp = H + 2, cpg = C / 32, C4 = C / 4;
+    __shared__ float s_mean[32], s_rstd[32];
+    if (threadIdx.x < 32) {
+        const double cnt = (double)H * W * cpg;
+        const double mean = stats[((size_t)b * 32 + threadIdx.x) * 2] / cnt;
+        const double var = stats[((size_t)b * 32 + threadIdx.x) * 2 + 1] / cnt - mean * mean;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const bool row_in = yy >= 1 && yy <= H;
+    const size_t row_base = ((size_t)b * Hp + yy) * Wp;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (int j = threadIdx.x; j < Wp * C4; j += blockDim.x) {
+        const int xx = j / C4, c4 = j - xx * C4;
+        const bool interior = row_in && xx >= 1 && xx <= W;
         if (!interior) {
-            if (!compact) y[src] = 0.f;
+            if (!compact) y4[(row_base + xx) * C4 + c4] = make_float4(0.f, 0.f, 0.f, 0.f);
             continue;
         }
-        const int g = ch / cpg;
-        const double mean = stats[((size_t)b * 32 + g) * 2] / cnt;
-        const double var = stats[((size_t)b * 32 + g) * 2 + 1] / cnt - mean * mean;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        float v = (x[src] - (float)mean) * rstd * gamma[ch] + beta[ch];
-        if (swish) v = v / (1.0f + expf(-v));
-        const size_t dst = compact ? ((size_t)b * H * W + (size_t)(yy - 1) * W + (xx - 1)) * C + ch : src;
-        y[dst] = v;
+        const float4 v = x4[(row_base + xx) * C4 + c4];
+        const float4 gm = g4[c4], bt = b4[c4];
+        const float in[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gm.x, gm.y, gm.z, gm.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = (c4 * 4 + k) / cpg;
+            float t = (in[k] - s_mean[g]) * s_rstd[g] * gg[k] + bb[k];
+            if (swish) t = t / (1.0f + expf(-t));
+            o[k] = t;
+        }
+        const size_t dst = compact ? ((size_t)b * H * W + (size_t)(yy - 1) * W + (xx - 1)) * C4 + c4 : (row_base + xx) * C4 + c4;
+        y4[dst] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -419,11 +436,8 @@ int gn_swish(const float* x, float* y, int B, int C, int H, int W, double* stats
         gn_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, C, H, W, stats_ws);
     }
     MMDP_CUDA(cudaGetLastError());
-    long long n = (long long)(H + 2) * (W + 2) * C;
-    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
-    if (blocks > 148 * 16) blocks = 148 * 16;
     LaunchScope ls(LK_ROW, (double)B * npix * C * 8, stream);
-    gn_apply_kernel<<<dim3(blocks, B), 256, 0, stream>>>(x, y, C, H, W, stats_ws, gamma, beta, eps, swish, compact);
+    gn_apply_kernel<<<dim3(H + 2, B), 256, 0, stream>>>(x, y, C, H, W, stats_ws, gamma, beta, eps, swish, compact);
     MMDP_CUDA(cudaGetLastError());
     return 0;
 }

@@ -31,7 +31,8 @@ template <int BN> struct GemmCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN == 256) ? 4 : 5;
-    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kScatBytes = 4 * kScatStageFloats * 4;  // staging of the fused reduce-scatter epilogue (EPI_F32)
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kScatBytes;
 };
 
 template <int EPI, int BN>
@@ -47,6 +48,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* scat_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -195,13 +197,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (old == S - 1) { p.sk_cnt[2 * unit_t] = 0; p.sk_cnt[2 * unit_t + 1] = 0; }
                 }
             }
-            if (run_epilogue) gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk);
+            if (run_epilogue) gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
             // all TMEM reads of this accumulator stage are complete (wait::ld above) -> hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
             if (++as == 2) { as = 0; aph ^= 1; }
             if (is_unit) break;
+        }
+        if constexpr (EPI == EPI_F32) {
+            if (p.scat_R > 0) __threadfence_system();  // the pushed rows are visible to their owners before this grid completes
         }
     }
 
@@ -320,7 +325,10 @@ void set_gemm_pair_mode(int on) { set_opt("gemm_pair", (on == 2) ? 2 : (on ? 1 :
 
 int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa,
-              cudaStream_t stream) {
+              cudaStream_t stream, const GemmScatter* sc) {
+    if (sc && epi != EPI_F32) return set_error("gemm: the scatter epilogue belongs to MMDP_EPI_F32");
+    if (sc && (sc->rows_per_rank <= 0 || sc->slot < 0 || sc->slot > 7 || (M + sc->rows_per_rank - 1) / sc->rows_per_rank > 8))
+        return set_error("gemm: bad scatter layout");
     if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm: empty problem");
     if ((lda % 8) || (ldw % 8) || (K % 8)) return set_error("gemm: lda/ldw/K must be multiples of 8 (16-byte TMA strides)");
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
@@ -334,7 +342,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
             if (!C || !resid || (ldc % 8) || (ldr % 8) || (N % 8)) return set_error("gemm: bad residual epilogue args");
             break;
         case EPI_F32:
-            if (!C || (ldc % 4) || (N % 4)) return set_error("gemm: fp32 output needs ldc/N multiples of 4");
+            if ((!C && !sc) || (ldc % 4) || (N % 4)) return set_error("gemm: fp32 output needs ldc/N multiples of 4");
             break;
         case EPI_SWIGLU:
             if (!C || (ldc % 8) || (N % 256)) return set_error("gemm: swiglu needs N % 256 == 0 (interleaved gate/up tiles)");
@@ -354,11 +362,17 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     // (profiles/r02). Small-M problems (the restricted LM head on 256 text rows) stay on the 1-CTA kernel below with its
     // split-K tail. 0 = always 1-CTA, 2 = pair only for M >= 4096 and N >= 8192.
     const int pm = gemm_pair_mode();
-    if ((pm == 1 && M > 256) || (pm == 2 && M >= 4096 && N >= 8192)) return gemm_bf16_pair(epi, A, lda, W, ldw, M, N, K, C, ldc, resid, ldr, qa, stream);
+    if ((pm == 1 && M > 256) || (pm == 2 && M >= 4096 && N >= 8192)) return gemm_bf16_pair(epi, A, lda, W, ldw, M, N, K, C, ldc, resid, ldr, qa, stream, sc);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
-    const GemmPlan pl = plan_gemm(epi, M, N, K);
+    GemmPlan pl = plan_gemm(epi, M, N, K);
+    if (sc) {
+        // the split-K tail finishes its tiles from the workspace into C; the scatter epilogue has no C - keep whole tiles
+        if (pl.tail > 0) { pl.tail = 0; pl.splits = 0; pl.kb_per = 0; const int t = ((M + BM - 1) / BM) * ((N + pl.bn - 1) / pl.bn); pl.grid = t < num_sms() ? t : num_sms(); }
+        for (int r = 0; r < 8; ++r) p.scat_dst[r] = sc->dst[r];
+        p.scat_R = sc->rows_per_rank; p.scat_slot = sc->slot;
+    }
     const int bn = pl.bn, grid = pl.grid;
     // tile order (gemm_tile_coords): with many m-tiles, walk them in balanced groups of <= 40 so that one wave of 148 tiles
     // spans ~30 m-tiles x ~5 n-tiles instead of all m-tiles x 2.6 n-tiles. Measured on M = 7242 (57 m-tiles, the B=3 batch

@@ -22,7 +22,7 @@ template <int BN> struct PairCfg {
     static constexpr int kBHalfBytes = (BN / 2) * P_BK * 2;
     static constexpr int kStageBytes = kPABytes + kBHalfBytes;  // per CTA
     static constexpr int kStages = (BN == 256) ? 6 : 7;
-    static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + 4 * kScatStageFloats * 4;  // + reduce-scatter staging
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -89,6 +89,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* scat_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -192,11 +193,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = m_blk * 2 * P_BM + (int)rank * P_BM + ew * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-            gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk);
+            gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
             if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if constexpr (EPI == EPI_F32) {
+            if (p.scat_R > 0) __threadfence_system();  // the pushed rows are visible to their owners before this grid completes
         }
     }
 
@@ -235,10 +239,15 @@ static int pick_pair_tile_n(int M, int N) {
 }
 
 int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
-                   __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa, cudaStream_t stream) {
+                   __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa, cudaStream_t stream,
+                   const GemmScatter* sc) {
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
+    if (sc) {
+        for (int r = 0; r < 8; ++r) p.scat_dst[r] = sc->dst[r];
+        p.scat_R = sc->rows_per_rank; p.scat_slot = sc->slot;
+    }
     const int bn = (epi == EPI_PLAIN || epi == EPI_RESID || epi == EPI_F32) ? pick_pair_tile_n(M, N) : 256;
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, P_BM, P_BK)) return -1;

@@ -28,6 +28,12 @@ struct GemmParams {
     int* sk_cnt;
     // L2 prefetch distance in k-blocks for the weight tiles (0 = off) and the share of CTAs issuing it (every l2pf_mod-th m-tile)
     int l2pf, l2pf_mod;
+    // EPI_F32 scatter (tensor parallel, GEMM fused with the reduce-scatter): scat_R > 0 -> the fp32 partial row `row` is
+    // not stored to C but PUSHED over NVLink into its owner's receive buffer, scat_dst[row / scat_R] (peer-mapped,
+    // [n_ranks][scat_R][ldc] fp32), slot scat_slot = this rank; rows staged through shared memory so that every store
+    // instruction writes whole 128-byte lines
+    float* scat_dst[8];
+    int scat_R, scat_slot;
     // tile order: group_m == 0 -> M-fastest over all m-tiles; > 0 -> M-fastest inside groups of group_m m-tiles, all n-tiles
     // of a group before the next group (keeps the group's A rows L2-resident while the weights stream)
     int group_m;
@@ -58,10 +64,39 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
 
 // tbase: TMEM address of this warp's lane quarter and accumulator stage; row: global output row of this thread;
 // n_blk: N-tile index (tile columns [n_blk*BN, n_blk*BN + BN)).
+static constexpr int kScatStageFloats = 32 * 36;  // per epilogue warp: 32 rows x 32 columns, row stride 36 floats (bank-conflict free)
+
 template <int EPI, int BN>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t tbase, int row, bool row_ok, int n_blk) {
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t tbase, int row, bool row_ok, int n_blk,
+                                                   float* stage = nullptr) {
             const int n0 = n_blk * BN;
             if constexpr (EPI == EPI_F32) {
+              if (p.scat_R > 0) {
+                // fused reduce-scatter: push this tile's partial rows to the ranks that own them
+                const int lane = threadIdx.x & 31;
+                const int row0 = row - lane;  // first row of this warp's 32 accumulator lanes
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tbase + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<uint4*>(stage + lane * 36 + i * 4) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    __syncwarp();
+                    const int col = n0 + c * 32 + (lane & 7) * 4;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = j * 4 + (lane >> 3), grow = row0 + r;
+                        if (grow < p.M && col < p.N) {
+                            const int owner = grow / p.scat_R;
+                            float* dst = p.scat_dst[owner] + ((size_t)p.scat_slot * p.scat_R + (grow - owner * p.scat_R)) * p.ldc + col;
+                            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stage + r * 36 + (lane & 7) * 4);
+                        }
+                    }
+                    __syncwarp();
+                }
+              } else {
                 // raw fp32 accumulators (tensor-parallel partial sums: reduced across ranks in fp32, rounded once afterwards)
                 float* Cf = reinterpret_cast<float*>(p.C);
 #pragma unroll 1
@@ -78,6 +113,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                             if (i * 4 < nvalid) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
+              }
             } else if constexpr (EPI == EPI_PLAIN || EPI == EPI_RESID) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {

@@ -103,13 +103,20 @@ struct QkvRopeArgs {
     int L, Lpad, d_model, n_heads;
 };
 
+// EPI_F32 only: push the fp32 partial rows to their owners' receive buffers instead of storing them to C (tensor parallel)
+struct GemmScatter {
+    float* dst[8];  // peer-mapped receive buffer of every rank: [n_ranks][rows_per_rank][ldc] fp32
+    int rows_per_rank, slot;
+};
+
 int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
               __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa,
-              cudaStream_t stream);
+              cudaStream_t stream, const GemmScatter* sc = nullptr);
 
 // CTA-pair (cta_group::2) kernel, gemm2.cu; selected by MMDP_GEMM_PAIR=1 or mmdp_set_gemm_pair(1)
 int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
-                   __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa, cudaStream_t stream);
+                   __nv_bfloat16* C, int ldc, const __nv_bfloat16* resid, int ldr, const QkvRopeArgs* qa, cudaStream_t stream,
+                   const GemmScatter* sc = nullptr);
 int gemm_pair_mode();
 void set_gemm_pair_mode(int on);
 int gemm_splitk_mode();
@@ -147,8 +154,8 @@ int image_step_t2i(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64
                    uint8_t* unknown_ws, uint8_t* masking_out, cudaStream_t stream);
 int lfq_decode(const int64_t* ids, float* zq, int B, int N, int bits, cudaStream_t stream);
 // tensor-parallel collective over NVLink peer memory (tp_collective.cu)
-int tp_reduce_norm(const float* const* part, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks, int my_rank,
-                   uint16_t* x_shard, const uint16_t* w, int row0, int nrows, int d, float eps, uint32_t epoch,
+int tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks,
+                   int my_rank, uint16_t* x_shard, const uint16_t* w, int row0, int nrows, int d, float eps, uint32_t epoch,
                    unsigned int* done_counter, cudaStream_t stream);
 
 }  // namespace mmdp

@@ -1,10 +1,11 @@
 // Tensor-parallel collective of the single-sample forward (BASELINE config 4), written against NVLink peer memory instead of
-// NCCL: the two row-parallel GEMMs of a layer (attn_out, ff_out; modeling_llada.py:744, :968) leave fp32 PARTIAL sums
-// [M, d] in a buffer every peer can read; what follows them in the reference - residual add (:953 / :970), the next
-// RMSLayerNorm (:315-329) and the broadcast of its output to all ranks - is ONE kernel per rank:
+// NCCL. Rank r owns the rows [r*R, (r+1)*R) of the residual stream (R = ceil(M / TP)). The two row-parallel GEMMs of a
+// layer (attn_out, ff_out; modeling_llada.py:744, :968) PUSH their fp32 partial rows from the epilogue straight into the
+// owner's receive buffer over NVLink (gemm_epilogue.cuh, EPI_F32 scatter: the reduce-scatter is fused into the GEMM and
+// overlaps its main loop; pulls over NVLink measured 2-3x slower than pushes). What follows in the reference - residual add
+// (:953 / :970), the next RMSLayerNorm (:315-329) and the broadcast of its output to all ranks - is ONE kernel per rank:
 //
-//   rank r owns the rows [r*R, (r+1)*R) of the residual stream (R = ceil(M / TP)) and, for each of them,
-//     sum   = part_0[row] + part_1[row] + ... + part_{TP-1}[row]      fp32, fixed rank order (P2P loads over NVLink)
+//     sum   = part_0[row] + part_1[row] + ... + part_{TP-1}[row]      fp32, fixed rank order (local loads of the pushed rows)
 //     x     = bf16( bf16(sum) + x )                                   the single-GPU rounding points of EPI_RESID
 //     xn    = bf16( w * bf16( x * rsqrt(mean(x^2) + eps) ) )          RMSLayerNorm with the next norm's weight
 //     xn -> every rank's activation buffer                            P2P stores over NVLink (the all-gather)
@@ -26,7 +27,8 @@ static constexpr int kTpMaxRanks = 8;
 static constexpr int kTpThreads = 256;
 
 struct TpReduceArgs {
-    const float* part[kTpMaxRanks];      // partial sums of every rank, peer-mapped; [M, d] fp32 (unused when n_src == 0)
+    const float* part[kTpMaxRanks];      // partial sums of every rank FOR THIS RANK'S ROWS: slot r of the local receive buffer,
+                                         // [rows_per_rank, d] fp32, pushed there by rank r's GEMM epilogue (unused when n_src == 0)
     __nv_bfloat16* xn[kTpMaxRanks];      // activation buffer of every rank, peer-mapped; [M, d] bf16
     uint32_t* flags[kTpMaxRanks];        // flag array of every rank, peer-mapped; [2][kTpMaxRanks] uint32
     int n_ranks, n_src, my_rank;
@@ -46,7 +48,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// peer data must not be served from this SM's (incoherent) L1: volatile 16-byte load
+// data written by a peer GPU into this GPU's memory must not be served from this SM's (incoherent) L1: volatile 16-byte load
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     float4 v;
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_norm_kernel(TpReduceArgs
 #pragma unroll
             for (int r = 0; r < kTpMaxRanks; ++r)
                 if (r < a.n_src) {
-                    p0[r] = ld_peer_f4(a.part[r] + grow + c);
-                    p1[r] = ld_peer_f4(a.part[r] + grow + c + 4);
+                    p0[r] = ld_peer_f4(a.part[r] + (size_t)lrow * a.d + c);
+                    p1[r] = ld_peer_f4(a.part[r] + (size_t)lrow * a.d + c + 4);
                 }
 #pragma unroll
             for (int r = 0; r < kTpMaxRanks; ++r)
@@ -166,16 +168,17 @@ __global__ void tp_wait_kernel(const uint32_t* flags_local, int phase, int n_ran
     tp_wait_flags(flags_local, phase, n_ranks, epoch);
 }
 
-int tp_reduce_norm(const float* const* part, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks, int my_rank,
-                   uint16_t* x_shard, const uint16_t* w, int row0, int nrows, int d, float eps, uint32_t epoch,
+int tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks,
+                   int my_rank, uint16_t* x_shard, const uint16_t* w, int row0, int nrows, int d, float eps, uint32_t epoch,
                    unsigned int* done_counter, cudaStream_t stream) {
     if (n_ranks < 1 || n_ranks > kTpMaxRanks || my_rank < 0 || my_rank >= n_ranks) return set_error("tp_reduce_norm: bad rank layout");
     if (n_src != 0 && n_src != n_ranks) return set_error("tp_reduce_norm: n_src must be 0 (no partial sums) or n_ranks");
+    if (n_src && (!recv_local || nrows > rows_per_rank)) return set_error("tp_reduce_norm: receive buffer / rows_per_rank mismatch");
     if (nrows <= 0) return set_error("tp_reduce_norm: every rank must own at least one row (M >= n_ranks)");
     if (d % 8 || d > 8192) return set_error("tp_reduce_norm: d must be a multiple of 8 and <= 8192");
     TpReduceArgs a{};
     for (int r = 0; r < n_ranks; ++r) {
-        a.part[r] = n_src ? part[r] : nullptr;
+        a.part[r] = n_src ? recv_local + (size_t)r * rows_per_rank * d : nullptr;
         a.xn[r] = reinterpret_cast<__nv_bfloat16*>(xn[r]);
         a.flags[r] = flags[r];
     }

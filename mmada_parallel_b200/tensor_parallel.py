@@ -5,10 +5,12 @@ GPUs of one node. The reference has no tensor parallelism; this f
     column-parallel, ff_out row-parallel); LM head: vocabulary rows split (and the VQ-codebook window split separately);
   * the two row-parallel GEMMs per layer produce fp32 PARTIAL sums (MMDP_EPI_F32). What follows them - the cross-rank sum,
     the residual add, the NEXT RMSNorm and the distribution of its output to all ranks - is one kernel per rank over NVLink
-    peer memory (`mmdp_tp_reduce_norm`, csrc/tp_collective.cu): every rank reduces the rows it owns in fixed rank order,
-    applies the single-GPU rounding points `x = bf16(bf16(sum) + x)` and the norm, and stores the bf16 result into every
-    rank's activation buffer. The residual stream is therefore row-sharded (M / TP rows per rank), the normalised activations
-    are replicated; 0.75x the bytes of an fp32 all-reduce and no separate residual / RMSNorm launches;
+    peer memory: the GEMM's epilogue PUSHES every fp32 partial row into the receive buffer of the rank that owns it
+    (`mmdp_gemm_f32_scatter`: the reduce-scatter is fused into the GEMM and overlaps its main loop), then
+    `mmdp_tp_reduce_norm` (csrc/tp_collective.cu) sums the rows a rank owns in fixed rank order, applies the single-GPU
+    rounding points `x = bf16(bf16(sum) + x)` and the norm, and stores the bf16 result into every rank's activation buffer
+    (the all-gather). The residual stream is row-sharded (M / TP rows per rank), the normalised activations are replicated;
+    0.75x the bytes of an fp32 all-reduce, all of them NVLink writes, and no separate residual / RMSNorm launches;
   * every rank gathers the logits slices it needs (NCCL all_gather, once per forward) and runs the SAME sampling kernels on
     the same noise (identical generator seeds), so the id sequence stays in sync without broadcasts.
 
@@ -65,11 +67,17 @@ def shard_state_dict(sd: Dict[str, torch.Tensor], n_layers: int, n_heads: int, r
     return out
 
 
+def rows_per_rank(M: int, tp: int) -> int:
+    return (M + tp - 1) // tp
+
+
 def row_partition(M: int, tp: int, rank: int):
-    """Rows of the residual stream rank `rank` owns: the balanced split [rank * M // tp, (rank + 1) * M // tp) - every
-    rank owns at least one row when M >= tp."""
-    r0 = rank * M // tp
-    return r0, (rank + 1) * M // tp - r0
+    """Rows of the residual stream rank `rank` owns: [rank * R, min((rank + 1) * R, M)) with R = ceil(M / tp) - the owner of a
+    row is row // R, which the GEMM's scatter epilogue evaluates per row. Returns (first row, count); the count of the last
+    ranks can be 0 for tiny M (rejected by the caller: every rank has to take part in the collective)."""
+    R = rows_per_rank(M, tp)
+    r0 = rank * R
+    return r0, max(0, min(R, M - r0))
 
 
 class _DeviceArray:
@@ -157,11 +165,12 @@ class TensorParallelLLaDA:
         if self.collective == "p2p":
             if M < tp_size:
                 raise ValueError("the workspace must hold at least one row per rank")
-            self._part = [_SharedBuffer(M * d * 4, tp_rank, tp_size, group) for _ in range(2)]   # used alternately
+            # receive buffers [tp][R][d] fp32 (slot r <- rank r's partial rows for the rows this rank owns), used alternately
+            self._recv = [_SharedBuffer(tp_size * rows_per_rank(M, tp_size) * d * 4, tp_rank, tp_size, group) for _ in range(2)]
             self._xn = _SharedBuffer(M * d * 2, tp_rank, tp_size, group)
             self._flags = _SharedBuffer(2 * 8 * 4, tp_rank, tp_size, group)
             self.xn = torch.as_tensor(_DeviceArray(self._xn.own, M * d, "<u2"), device=self.device).view(torch.bfloat16).view(M, d)
-            self.x = torch.empty(((M + tp_size - 1) // tp_size + 1, d), **bf)                    # this rank's rows of the residual stream
+            self.x = torch.empty((rows_per_rank(M, tp_size), d), **bf)                            # this rank's rows of the residual stream
             self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._epoch = 0
             torch.cuda.synchronize()
@@ -172,7 +181,7 @@ class TensorParallelLLaDA:
             self.part = torch.empty((M, d), dtype=torch.float32, device=self.device)
 
     def __del__(self):
-        for b in getattr(self, "_part", []) + [getattr(self, "_xn", None), getattr(self, "_flags", None)]:
+        for b in getattr(self, "_recv", []) + [getattr(self, "_xn", None), getattr(self, "_flags", None)]:
             if b is not None:
                 try:
                     b.close()
@@ -197,15 +206,25 @@ class TensorParallelLLaDA:
         out.view(n, self.tp, c).copy_(buf.permute(1, 0, 2))
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _reduce_norm(self, part_idx: Optional[int], weight: torch.Tensor, M: int):
-        """Cross-rank sum of the fp32 partials (part_idx None: no partials), residual add on this rank's rows, RMSNorm with
-        `weight`, result into every rank's xn; on return (in stream order) all M rows of self.xn are valid."""
+    def _reduce_norm(self, recv_idx: Optional[int], weight: torch.Tensor, M: int):
+        """Sum of the fp32 partial rows the ranks pushed into receive buffer `recv_idx` (None: no partials), residual add on
+        this rank's rows, RMSNorm with `weight`, result into every rank's xn; on return (in stream order) all M rows of
+        self.xn are valid."""
         self._epoch += 1
         r0, nrows = row_partition(M, self.tp, self.rank)
-        part = self._part[part_idx].array if part_idx is not None else None
-        check(lib.mmdp_tp_reduce_norm(part, self.tp if part_idx is not None else 0, self._xn.array, self._flags.array, self.tp, self.rank,
-                                      ptr(self.x), ptr(weight), r0, nrows, self.d_model, self.rms_eps, self._epoch, ptr(self._done),
-                                      stream_ptr()))
+        recv = self._recv[recv_idx].own if recv_idx is not None else None
+        check(lib.mmdp_tp_reduce_norm(recv, rows_per_rank(M, self.tp), self.tp if recv_idx is not None else 0, self._xn.array,
+                                      self._flags.array, self.tp, self.rank, ptr(self.x), ptr(weight), r0, nrows, self.d_model,
+                                      self.rms_eps, self._epoch, ptr(self._done), stream_ptr()))
+
+    def _row_parallel_gemm(self, a: torch.Tensor, wt: torch.Tensor, K: int, M: int, recv_idx: int):
+        """fp32 partial sums of a row-parallel linear: pushed to the owners (p2p) or stored locally for the NCCL all-reduce."""
+        d, s = self.d_model, stream_ptr()
+        if self.collective == "p2p":
+            check(lib.mmdp_gemm_f32_scatter(ptr(a), K, ptr(wt), K, M, d, K, self._recv[recv_idx].array, self.tp,
+                                            rows_per_rank(M, self.tp), self.rank, s))
+        else:
+            check(lib.mmdp_gemm_bf16(EPI_F32, ptr(a), K, ptr(wt), K, M, d, K, ptr(self.part), d, None, 0, s))
 
     def _layers(self, B: int, L: int, M: int, Lpad: int):
         d, s, w = self.d_model, stream_ptr(), self.w
@@ -219,9 +238,7 @@ class TensorParallelLLaDA:
             check(lib.mmdp_qkv_rope_tp(ptr(xn), d, ptr(w[p + "wqkv"]), M, d, self.h_local, L, Lpad, ptr(self.cos), ptr(self.sin),
                                        ptr(self.q), ptr(self.k), ptr(self.vt), s))
             check(lib.mmdp_attention(ptr(self.q), ptr(self.k), ptr(self.vt), ptr(self.att), B, self.h_local, L, Lpad, scale, s))
-            part = self._part[0].own if p2p else ptr(self.part)
-            check(lib.mmdp_gemm_bf16(EPI_F32, ptr(self.att), self.d_attn, ptr(w[p + "wo"]), self.d_attn, M, d, self.d_attn,
-                                     part, d, None, 0, s))
+            self._row_parallel_gemm(self.att, w[p + "wo"], self.d_attn, M, 0)
             if p2p:
                 self._reduce_norm(0, w[p + "ff_norm"], M)
             else:
@@ -230,9 +247,7 @@ class TensorParallelLLaDA:
                 check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "ff_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
             check(lib.mmdp_gemm_bf16(EPI_SWIGLU, ptr(xn), d, ptr(w[p + "w13"]), d, M, 2 * self.ff_local, d, ptr(self.h),
                                      self.ff_local, None, 0, s))
-            part = self._part[1].own if p2p else ptr(self.part)
-            check(lib.mmdp_gemm_bf16(EPI_F32, ptr(self.h), self.ff_local, ptr(w[p + "w2"]), self.ff_local, M, d, self.ff_local,
-                                     part, d, None, 0, s))
+            self._row_parallel_gemm(self.h, w[p + "w2"], self.ff_local, M, 1)
             if p2p:
                 nxt = w[f"blocks.{i + 1}.attn_norm"] if i + 1 < self.n_layers else w["ln_f"]
                 self._reduce_norm(1, nxt, M)
@@ -252,8 +267,8 @@ class TensorParallelLLaDA:
             self._vt_key = (B, Lpad, L)
         wte = self.w["wte"]
         if self.collective == "p2p":
-            if M < self.tp:
-                raise _lib.MmdpError("TensorParallelLLaDA: needs at least one token per rank")
+            if row_partition(M, self.tp, self.tp - 1)[1] < 1:
+                raise _lib.MmdpError(f"TensorParallelLLaDA: {M} tokens cannot be split over {self.tp} ranks with at least one row each")
             r0, nrows = row_partition(M, self.tp, self.rank)
             check(lib.mmdp_embed(ids.data_ptr() + r0 * 8, ptr(wte), ptr(self.x), nrows, d, wte.shape[0], s))   # this rank's rows only
             self._reduce_norm(None, self.w["blocks.0.attn_norm"], M)

@@ -162,14 +162,15 @@ def test_preview_host_helpers_match_oracle():
 
 
 def test_tensor_parallel_row_partition():
-    """Rows of the residual stream owned per rank (tensor_parallel.row_partition): disjoint, in order, covering [0, M), and
-    at least one row per rank whenever M >= tp (the peer-memory collective needs every rank to signal)."""
-    from mmada_parallel_b200.tensor_parallel import row_partition
-    for M in (8, 9, 77, 2414, 4682, 4096):
+    """Rows of the residual stream owned per rank (tensor_parallel.row_partition): disjoint, in order, covering [0, M), owner
+    of a row = row // rows_per_rank (what the GEMM's scatter epilogue evaluates), at most rows_per_rank rows each."""
+    from mmada_parallel_b200.tensor_parallel import row_partition, rows_per_rank
+    for M in (8, 9, 64, 77, 2414, 4682, 4096):
         for tp in (1, 2, 4, 8):
+            R = rows_per_rank(M, tp)
             parts = [row_partition(M, tp, r) for r in range(tp)]
             assert parts[0][0] == 0 and sum(n for _, n in parts) == M
-            for (a0, an), (b0, _) in zip(parts, parts[1:]):
-                assert a0 + an == b0
-            assert all(n >= 1 for _, n in parts)
-            assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+            for r, (r0, n) in enumerate(parts):
+                assert 0 <= n <= R
+                assert all(row // R == r for row in (r0, r0 + n - 1)) if n else True
+    assert row_partition(2414, 8, 7) == (2114, 300)

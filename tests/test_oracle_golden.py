@@ -221,3 +221,18 @@ def test_variant_m_modes_match_reference_golden(tiny):
                                          mask_id=126336, num_vq_tokens=16, codebook_size=8192, max_seq_length=12, text_vocab_len=tv,
                                          generator=torch.Generator().manual_seed(r["seed"]), **r["kwargs"])
         assert torch.equal(img, r["image_ids"]) and torch.equal(txt, r["text_ids"]), r["name"]
+
+
+def test_separated_model_trajectories_match_reference_golden():
+    """The "well-separated" tiny model (oracle/make_golden_separated.py): the oracle reproduces the REAL reference's per-step ids
+    on all three configurations (greedy / bench-like / both CFGs + text Gumbel) - the fixture the B200 path must match bit for
+    bit in tests/test_gpu_model.py::test_trajectory_bit_equal_to_reference_on_separated_model."""
+    from oracle.make_golden_separated import separated_weights, trajectory
+    t = load_golden("trajectory_a_separated.pt")
+    cfg = llada.make_config(**t["meta"]["tiny"])
+    for run in t["runs"]:
+        sd, _ = separated_weights(cfg, run["weight_seed"])
+        img, txt, tr = trajectory(llada.OracleModel(cfg, sd), t["layout"], run["kwargs"], run["seed"], run["global_seed"])
+        assert img == run["image_tokens"] and txt == run["text_tokens"], run["name"]
+        for step, rec in enumerate(tr):
+            assert torch.equal(rec["ids_after_text"], run["ids_after_text"][step])
