@@ -374,14 +374,22 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     const int n_qt = (L + 127) / 128, n_kvb = (L + k6BKV - 1) / k6BKV;
     const int tiles = n_qt * H * B, slots = 2 * num_sms();
     int n_full = tiles, n_split = 0, splits = 1;
+    auto fit_splits = [&](int want) {
+        int sp = want > 8 ? 8 : want;
+        if (sp > n_kvb / 2) sp = n_kvb / 2;
+        // no empty piece: piece i covers KV blocks [i * per, (i + 1) * per) with per = ceil(n_kvb / splits)
+        while (sp >= 2 && (sp - 1) * ((n_kvb + sp - 1) / sp) >= n_kvb) --sp;
+        return sp;
+    };
     if (split_tail && tiles > slots && (tiles % slots) > 0 && (tiles % slots) * 4 <= slots) {
         n_split = tiles % slots;
-        splits = slots / n_split;
-        if (splits > 8) splits = 8;
-        if (splits > n_kvb / 2) splits = n_kvb / 2;
-        // no empty piece: piece i covers KV blocks [i * per, (i + 1) * per) with per = ceil(n_kvb / splits)
-        while (splits >= 2 && (splits - 1) * ((n_kvb + splits - 1) / splits) >= n_kvb) --splits;
+        splits = fit_splits(slots / n_split);
         if (splits >= 2) n_full = tiles - n_split; else { n_split = 0; splits = 1; }
+    } else if (split_tail && tiles * 2 <= slots) {
+        // fewer tiles than half the CTA slots (a tensor-parallel rank with 4 of the 32 heads: 76 tiles on 296 slots): split EVERY
+        // tile's KV range so that the whole machine works on the launch
+        splits = fit_splits(slots / tiles);
+        if (splits >= 2) { n_split = tiles; n_full = 0; } else splits = 1;
     }
     float* part_ws = nullptr;
     if (n_split > 0 && attn_part_workspace(stream, (size_t)n_split * splits * (128 * 128 + 256) * sizeof(float), &part_ws)) return -1;

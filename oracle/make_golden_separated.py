@@ -7,7 +7,7 @@ allows"). Writes tests/golden/trajectory_a_separated.pt.
 
 Construction: the tiny LLaDA of the other fixtures, but the LM head keeps only a few LIVE rows (24 text tokens, 16 VQ codes,
 gain 4); every other row is scaled by 1e-3, so logits have a handful of well-spread candidates instead of 134 656 near-ties.
-A seed is accepted when the oracle trajectory is unchanged under 8 independent perturbations of the logits by +-2 bf16 ulp of
+A seed is accepted when the oracle trajectory is unchanged under 8 independent perturbations of the logits by +-3 bf16 ulp of
 the logit scale (the GPU test first checks that its logits are inside this radius of the oracle's; measured error is well below 1 ulp; dead rows are perturbed in proportion to their row
 norm, as accumulation error is) - every decision (argmax, top-k confidence rank, sampling race, re-mask cut) then has more than
 that margin with overwhelming probability. The accepted configuration is run through the REAL reference, which must agree
@@ -29,7 +29,7 @@ N_LIVE_TEXT, N_LIVE_VQ, GAIN, DEAD = 24, 16, 4.0, 1e-3
 RUNS = [("greedy", dict(text_steps=4, timesteps=2, text_gen_length=8, temperature=0.0, text_temperature=0.0, cfg_scale=0.0, cfg_img=4.0)),
         ("bench_like", dict(text_steps=4, timesteps=2, text_gen_length=8, temperature=1.0, text_temperature=0.0, cfg_scale=0.0, cfg_img=4.0)),
         ("both_cfg_gumbel", dict(text_steps=4, timesteps=2, text_gen_length=8, temperature=0.8, text_temperature=0.5, cfg_scale=1.5, cfg_img=3.0))]
-PERTURB_ULPS = 2.0   # the GPU forward is held to 4 bf16 ulp of the logit scale in general and measured far below 1; the test re-checks <= 2 on this model
+PERTURB_ULPS = 3.0   # measured GPU error on these models: up to 2.5 bf16 ulp of the logit scale (a single bf16 rounding step of the largest logits is already 1.6); the test re-checks <= 3
 
 
 def separated_weights(cfg, seed: int):
@@ -78,7 +78,7 @@ def main():
     out = dict(meta=dict(tiny=TINY, n_live_text=N_LIVE_TEXT, n_live_vq=N_LIVE_VQ, gain=GAIN, dead=DEAD, layout_seed=5, perturb_ulps=PERTURB_ULPS, layout=dict(prompt_len=6, grid=3, text_len=8)), runs=[])
     for name, kw in RUNS:
         found = None
-        for wseed in range(4000, 4400):
+        for wseed in range(4000, 6000):
             sd, gain = separated_weights(cfg, wseed)
             om = llada.OracleModel(cfg, sd)
             img, txt, tr = trajectory(om, lay, kw, seed=wseed + 1, global_seed=wseed + 2)
