@@ -263,6 +263,15 @@ MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L,
 
 /* Debug/testing: copy of the residual stream after `layer` layers is kept when enabled (device pointer returned). */
 MMDP_API const uint16_t* mmdp_model_hidden(mmdp_model* m);
+/* Token-cache forward: LLaDAModelLM.forward(input_ids, use_cache=True, to_compute_mask=mask, cat=key)
+ * (MMaDA-Parallel-A/model/modeling_llada.py:1244-1245, :929-940, :715-716, :1406-1413). Computes the Tq selected tokens of every
+ * batch row against the FULL cached key / value set and refreshes the caches at their positions first:
+ *   ids [B*Tq] ids of the selected tokens (batch-row major); pos_map [B*Tq] their sequence positions (int32), or NULL with
+ *   Tq == L for a full forward that fills the caches; kcache [n_layers][B*L][d] bf16 (keys after rotary); vtcache
+ *   [n_layers][B][H][128][Lpad] bf16 (values transposed, Lpad = L rounded up to 8, pad columns zero - allocate zeroed);
+ *   logits (nullable) [B*Tq][V] bf16 of the selected tokens. The caches are owned by the caller, one set per `cat` key. */
+MMDP_API int mmdp_model_forward_cached(mmdp_model* m, const int64_t* ids, int B, int L, int Tq, const int32_t* pos_map, uint16_t* kcache,
+                              uint16_t* vtcache, uint16_t* logits, void* stream);
 /* Sticky device-side error flags of the forwards issued so far, read and cleared (this call SYNCHRONISES `stream`):
  * bit 0 = a token id was outside [0, vocab_size) (torch raises IndexError in nn.Embedding; the kernel read row 0),
  * bit 1 = a logits row index (rows_a / rows_b) was outside [0, B*L). The host mirrors call it at their read-back point. */

@@ -399,4 +399,51 @@ MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L,
     return 0;
 }
 
+// Token-cache forward (reference: LLaDAModelLM.forward(input_ids, use_cache=True, to_compute_mask=mask, cat=key),
+// MMaDA-Parallel-A/model/modeling_llada.py:1244-1245 (ids restricted to the masked positions), :929-940 (per-block k / v caches,
+// scattered at the recomputed positions), :715-716 + :412-435 (rotary with the recomputed tokens' own positions for q, all
+// positions for k), :1406-1413 (logit cache). One call computes the Tq selected tokens of every batch row against the FULL
+// cached key/value set:
+//   ids       [B * Tq]      the selected tokens' ids, batch row major (pos_map == NULL: Tq == L, every token - a full forward)
+//   pos_map   [B * Tq]      their positions inside the sequence (int32; increasing per batch row), or NULL
+//   kcache    [n_layers][B * L][d]            keys AFTER rotary (rope(k, pos) is a function of the cached value and its
+//                                              position only, so caching it is equivalent to the reference's rope of the cached k)
+//   vtcache   [n_layers][B][H][128][Lpad]     values, transposed; pad columns must be zero (Lpad = L rounded up to 8)
+//   logits    [B * Tq][V]   logits of the selected tokens (the caller scatters them into its logit cache)
+// The selected tokens' k / v^T are written into the caches at their positions before attention, like the reference does.
+MMDP_API int mmdp_model_forward_cached(mmdp_model* m, const int64_t* ids, int B, int L, int Tq, const int32_t* pos_map, uint16_t* kcache,
+                              uint16_t* vtcache, uint16_t* logits, void* stream) {
+    if (!m || !ids || !kcache || !vtcache) return set_error("mmdp_model_forward_cached: null argument");
+    const mmdp_model_config& c = m->cfg;
+    if (B <= 0 || B > c.max_batch || L <= 0 || L > c.max_seq_len || Tq <= 0 || Tq > L)
+        return set_error("mmdp_model_forward_cached: B=%d L=%d Tq=%d outside workspace (max_batch=%d max_seq_len=%d)", B, L, Tq, c.max_batch, c.max_seq_len);
+    if (!pos_map && Tq != L) return set_error("mmdp_model_forward_cached: a partial forward needs the position map");
+    if (L > m->rope_len) return set_error("mmdp_model_forward_cached: rotary table covers %d positions, need %d", m->rope_len, L);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int d = c.d_model, ff = c.mlp_hidden, V = c.vocab_size, H = c.n_heads;
+    const int M = B * Tq;
+    const int Lpad = ((L + 7) / 8) * 8;
+    const float scale = 1.0f / sqrtf(128.0f);
+    const size_t k_layer = (size_t)B * L * d, vt_layer = (size_t)B * d * Lpad;
+    if (embed_rows(ids, m->wte, m->x, M, d, V, s, m->err_flag)) return -1;
+    for (int li = 0; li < c.n_layers; ++li) {
+        const LayerWeights& l = m->layers[li];
+        bf16* kc = (bf16*)kcache + (size_t)li * k_layer;
+        bf16* vc = (bf16*)vtcache + (size_t)li * vt_layer;
+        QkvRopeArgs qa{m->q, kc, vc, m->cos_tab, m->sin_tab, L, Lpad, d, H, pos_map, pos_map ? Tq : 0};
+        if (rmsnorm(m->x, d, l.attn_norm, m->xn, d, M, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_QKVROPE, m->xn, d, l.wqkv, d, M, 3 * d, d, nullptr, 0, nullptr, 0, &qa, s)) return -1;
+        if (attention_fwd(m->q, kc, vc, m->att, B, H, L, Lpad, scale, s, Tq)) return -1;
+        if (gemm_bf16(EPI_RESID, m->att, d, l.wo, d, M, d, d, m->x, d, m->x, d, nullptr, s)) return -1;
+        if (rmsnorm(m->x, d, l.ff_norm, m->xn, d, M, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_SWIGLU, m->xn, d, l.w13, d, M, 2 * ff, d, m->h, ff, nullptr, 0, nullptr, s)) return -1;
+        if (gemm_bf16(EPI_RESID, m->h, ff, l.w2, ff, M, d, ff, m->x, d, m->x, d, nullptr, s)) return -1;
+    }
+    if (logits) {
+        if (rmsnorm(m->x, d, m->ln_f, m->xn, d, M, d, c.rms_eps, s)) return -1;
+        if (gemm_bf16(EPI_PLAIN, m->xn, d, m->head, d, M, V, d, (bf16*)logits, V, nullptr, 0, nullptr, s)) return -1;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -44,7 +44,7 @@ template <int POLY>
 __global__ void __launch_bounds__(k6Threads, 2)
 attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
-                    float scale_log2, int n_full, int splits, float* __restrict__ part_ws) {
+                    float scale_log2, int n_full, int splits, float* __restrict__ part_ws, int Lq) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
@@ -70,7 +70,8 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // work items: [0, n_full) whole (b, h, query tile) problems; then, for each of the remaining tiles (the partial last wave),
     // `splits` pieces that each cover a slice of the KV blocks and leave an un-normalised partial (O, m, l) in part_ws for
     // attention_combine_kernel. tile index = (b * H + h) * n_qt + qt.
-    const int n_qt = (L + 127) / 128;
+    // L = number of keys per batch row; Lq = number of query rows per batch row (== L except in the token-cache forward)
+    const int n_qt = (Lq + 127) / 128;
     const int n_kv_all = (L + k6BKV - 1) / k6BKV;
     int tile = blockIdx.x, piece = -1;
     if ((int)blockIdx.x >= n_full) {
@@ -124,7 +125,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 4) {
         // ===================== TMA producer: Q, then the K tiles =====================
         if (elect_one_sync()) {
-            const int qrow0 = b * L + qt * 128;
+            const int qrow0 = b * Lq + qt * 128;
             mbar_expect_tx(q_full, k6QBytes);
             tma_load_2d(sQ, &tmQ, q_full, h * 128, qrow0);
             tma_load_2d(sQ + k6QBytes / 2, &tmQ, q_full, h * 128 + 64, qrow0);
@@ -269,7 +270,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (piece >= 0) {
             // partial result of this KV slice: O un-normalised (scaled by 2^(-m_used c)), m_used, l - merged by the combine kernel
             float* slot = part_ws + (size_t)((tile - n_full) * splits + piece) * (128 * 128 + 256);
-            if (qrow < L) {
+            if (qrow < Lq) {
                 slot[128 * 128 + r] = m_used;
                 slot[128 * 128 + 128 + r] = l_run;
             }
@@ -278,7 +279,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
                 tmem_ld_wait();
-                if (qrow < L) {
+                if (qrow < Lq) {
                     uint4* d4 = reinterpret_cast<uint4*>(slot + (size_t)r * 128 + c * 32);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -286,13 +287,13 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         } else {
             const float inv_l = 1.0f / l_run;
-            __nv_bfloat16* orow = out + (size_t)(b * L + (qrow < L ? qrow : 0)) * d_model + h * 128;
+            __nv_bfloat16* orow = out + (size_t)(b * Lq + (qrow < Lq ? qrow : 0)) * d_model + h * 128;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tO + lane_off + c * 32, v);
                 tmem_ld_wait();
-                if (qrow < L) {
+                if (qrow < Lq) {
                     uint32_t o[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
@@ -315,16 +316,16 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // Merges the `splits` KV-slice partials of one split tile: out = (sum_i w_i O_i) / (sum_i w_i l_i), w_i = 2^((m_i - m) c).
 // One CTA per (split tile, query row), thread = output column.
 __global__ void __launch_bounds__(128)
-attention_combine_kernel(const float* __restrict__ part_ws, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
+attention_combine_kernel(const float* __restrict__ part_ws, __nv_bfloat16* __restrict__ out, int H, int Lq, int d_model,
                          float scale_log2, int n_full, int splits) {
-    const int n_qt = (L + 127) / 128;
+    const int n_qt = (Lq + 127) / 128;
     const int st = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
     const int tile = n_full + st;
     const int qt = tile % n_qt, h = (tile / n_qt) % H, b = tile / (n_qt * H);
     const int qrow = qt * 128 + r;
-    if (qrow >= L) return;
+    if (qrow >= Lq) return;
     const float* base = part_ws + (size_t)st * splits * (128 * 128 + 256);
     float m = -INFINITY;
     for (int i = 0; i < splits; ++i) m = fmaxf(m, base[(size_t)i * (128 * 128 + 256) + 128 * 128 + r]);
@@ -335,7 +336,7 @@ attention_combine_kernel(const float* __restrict__ part_ws, __nv_bfloat16* __res
         o = fmaf(w, slot[(size_t)r * 128 + c], o);
         l = fmaf(w, slot[128 * 128 + 128 + r], l);
     }
-    out[(size_t)(b * L + qrow) * d_model + h * 128 + c] = __float2bfloat16_rn(o / l);
+    out[(size_t)(b * Lq + qrow) * d_model + h * 128 + c] = __float2bfloat16_rn(o / l);
 }
 
 // KV-slice partials of the split tail: one buffer per (device, stream), grown on demand
@@ -357,12 +358,13 @@ static int attn_part_workspace(cudaStream_t stream, size_t need, float** out) {
 }
 
 int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
-                     int Lpad, float scale, cudaStream_t stream) {
+                     int Lpad, float scale, cudaStream_t stream, int Lq) {
     if (B <= 0 || H <= 0 || L <= 0) return set_error("attention: empty problem");
+    if (Lq <= 0) Lq = L;
     if (Lpad < L || (Lpad % 8)) return set_error("attention: Lpad must be >= L and a multiple of 8");
     const int d_model = H * 128;
     CUtensorMap tmQ, tmK, tmVt;
-    if (make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, 128, 64)) return -1;
+    if (make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * Lq, (uint64_t)d_model, (uint64_t)d_model, 128, 64)) return -1;
     if (make_tmap_2d_bf16(&tmK, k, (uint64_t)B * L, (uint64_t)d_model, (uint64_t)d_model, k6BKV, 64)) return -1;
     if (make_tmap_2d_bf16(&tmVt, vt, (uint64_t)B * H * 128, (uint64_t)Lpad, (uint64_t)Lpad, 128, 64)) return -1;
     // share of exp2 evaluated on the FMA pipe: every POLY-th pair's second element (0 = none; default 4 = 1/8 of all exp2). MMDP_ATTN_POLY = 0|2|4|8.
@@ -371,7 +373,7 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     const int split_tail = opt(OPT_ATTN_SPLIT_TAIL);
     // Partial last wave: tiles % (2 CTAs x SMs) leftover tiles would run alone at the end (608 tiles on 296 slots: 30 % of the
     // launch at B=1). Split their KV range over the idle slots and merge the partials (attention_combine_kernel).
-    const int n_qt = (L + 127) / 128, n_kvb = (L + k6BKV - 1) / k6BKV;
+    const int n_qt = (Lq + 127) / 128, n_kvb = (L + k6BKV - 1) / k6BKV;
     const int tiles = n_qt * H * B, slots = 2 * num_sms();
     int n_full = tiles, n_split = 0, splits = 1;
     auto fit_splits = [&](int want) {
@@ -396,7 +398,7 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     const int grid = n_full + n_split * splits;
     const float scale_log2 = scale * 1.4426950408889634f;
     const bool pdl = pdl_mode() != 0;
-    LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)L * L * 128, stream);
+    LaunchScope ls(LK_ATTN, 4.0 * B * H * (double)Lq * L * 128, stream);
     auto launch = [&](auto kernel) -> int {
         static unsigned long long attr_set = 0;  // bit per device (one instantiation per POLY value)
         int dev = 0;
@@ -407,7 +409,7 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
             attr_set |= 1ull << (dev & 63);
         }
         MMDP_CUDA(launch_ex(kernel, dim3(grid), dim3(k6Threads), k6Smem, stream, pdl, false, tmQ, tmK, tmVt, out, H, L, d_model,
-                            scale_log2, n_full, splits, part_ws));
+                            scale_log2, n_full, splits, part_ws, Lq));
         return 0;
     };
     if (poly == 2) { if (launch(attention_v6_kernel<2>)) return -1; }
@@ -416,7 +418,7 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     else { if (launch(attention_v6_kernel<0>)) return -1; }
     MMDP_CUDA(cudaGetLastError());
     if (n_split > 0)
-        MMDP_CUDA(launch_ex(attention_combine_kernel, dim3(n_split, 128), dim3(128), 0, stream, pdl, false, (const float*)part_ws, out, H, L,
+        MMDP_CUDA(launch_ex(attention_combine_kernel, dim3(n_split, 128), dim3(128), 0, stream, pdl, false, (const float*)part_ws, out, H, Lq,
                             d_model, scale_log2, n_full, splits));
     return 0;
 }

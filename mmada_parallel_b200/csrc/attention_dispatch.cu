@@ -14,7 +14,7 @@ namespace mmdp {
 int attention_fwd_v3(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
                      int Lpad, float scale, cudaStream_t stream);
 int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
-                     int Lpad, float scale, cudaStream_t stream);
+                     int Lpad, float scale, cudaStream_t stream, int Lq);
 int attention_fwd_v5(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
                      int Lpad, float scale, cudaStream_t stream);
 
@@ -22,14 +22,15 @@ static int g_attn_version = -1;
 void set_attention_version(int v) { g_attn_version = v; }
 
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
-                  int Lpad, float scale, cudaStream_t stream) {
+                  int Lpad, float scale, cudaStream_t stream, int Lq) {
+    if (Lq > 0 && Lq != L) return attention_fwd_v6(q, k, vt, out, B, H, L, Lpad, scale, stream, Lq);  // only v6 separates query and key lengths
     if (g_attn_version < 0) {
         const char* e = getenv("MMDP_ATTN");
         g_attn_version = (e && e[0] == '3') ? 3 : (e && e[0] == '5') ? 5 : 6;
     }
     if (g_attn_version == 3) return attention_fwd_v3(q, k, vt, out, B, H, L, Lpad, scale, stream);
     if (g_attn_version == 5) return attention_fwd_v5(q, k, vt, out, B, H, L, Lpad, scale, stream);
-    return attention_fwd_v6(q, k, vt, out, B, H, L, Lpad, scale, stream);
+    return attention_fwd_v6(q, k, vt, out, B, H, L, Lpad, scale, stream, 0);
 }
 
 }  // namespace mmdp

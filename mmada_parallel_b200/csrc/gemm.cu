@@ -351,7 +351,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
             if (!qa) return set_error("gemm: qkv epilogue needs QkvRopeArgs");
             if (qa->d_model % 256 || N != 3 * qa->d_model || qa->d_model != qa->n_heads * 128)
                 return set_error("gemm: qkv epilogue needs head_dim 128, d_model % 256 == 0, N == 3*d_model");
-            if (M % qa->L) return set_error("gemm: qkv epilogue needs M == B*L");
+            if (qa->pos_map ? (qa->Tq <= 0 || M % qa->Tq) : (M % qa->L)) return set_error("gemm: qkv epilogue needs M == B*L (or B*Tq with a position map)");
             break;
         default:
             return set_error("gemm: unknown epilogue");
@@ -367,6 +367,11 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.resid = resid; p.ldr = ldr;
     GemmPlan pl = plan_gemm(epi, M, N, K);
+    if (qa && qa->pos_map && pl.tail > 0) {  // the split-K finishing pass addresses rows by sequence position only
+        pl.tail = 0; pl.splits = 0; pl.kb_per = 0;
+        const int t = ((M + BM - 1) / BM) * ((N + pl.bn - 1) / pl.bn);
+        pl.grid = t < num_sms() ? t : num_sms();
+    }
     if (sc) {
         // the split-K tail finishes its tiles from the workspace into C; the scatter epilogue has no C - keep whole tiles
         if (pl.tail > 0) { pl.tail = 0; pl.splits = 0; pl.kb_per = 0; const int t = ((M + BM - 1) / BM) * ((N + pl.bn - 1) / pl.bn); pl.grid = t < num_sms() ? t : num_sms(); }
@@ -414,6 +419,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
         case EPI_QKVROPE:
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
+            p.pos_map = qa->pos_map; p.Tq = qa->Tq;
             return launch_gemm<EPI_QKVROPE, 256>(tmA, tmB, p, grid, stream);
         default:
             return set_error("gemm: unknown epilogue");

@@ -19,6 +19,11 @@ struct GemmParams {
     const float* cos_tab;  // [L, 64]
     const float* sin_tab;  // [L, 64]
     int L, Lpad, d_model, n_heads;
+    // token-cache forward (modeling_llada.py:929-940): the GEMM rows are a COMPACT subset of the sequence - row r is token
+    // pos_map[r] of batch row r / Tq; q stays compact, k / v^T are scattered into the per-layer cache at that position.
+    // nullptr: row r is token r % L of batch row r / L
+    const int* pos_map;
+    int Tq;
     // split-K tail (gemm.cu): the last `sk_tail` tiles (a partial wave) are split along K into `sk_splits` (<= 8) units of
     // `sk_kb_per` k-blocks; partial accumulators meet in `sk_ws` (fp32, [tail][splits][BN/4][128] float4: column-group major,
     // tile row minor, so that both the publishing threads (thread = row) and the finishing threads (consecutive threads =
@@ -176,10 +181,17 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                 }
             } else if constexpr (EPI == EPI_QKVROPE) {
                 const int region = n0 / p.d_model;  // 0 = Q, 1 = K, 2 = V (d_model % 256 == 0 is checked on the host)
-                const int b = row_ok ? row / p.L : 0;
-                const int pos = row_ok ? row - b * p.L : 0;
+                int b, pos;
+                if (p.pos_map) {
+                    b = row_ok ? row / p.Tq : 0;
+                    pos = row_ok ? p.pos_map[row] : 0;
+                } else {
+                    b = row_ok ? row / p.L : 0;
+                    pos = row_ok ? row - b * p.L : 0;
+                }
                 if (region < 2) {
-                    __nv_bfloat16* dst = (region == 0 ? p.q : p.k) + (size_t)row * p.d_model + (n0 - region * p.d_model);
+                    const size_t drow = (region == 0 || !p.pos_map) ? (size_t)row : (size_t)b * p.L + pos;  // k rows go to their sequence position
+                    __nv_bfloat16* dst = (region == 0 ? p.q : p.k) + drow * p.d_model + (n0 - region * p.d_model);
 #pragma unroll 1
                     for (int hc = 0; hc < 4; ++hc) {  // (head in tile) x (32-col chunk of the first half)
                         const int head = hc >> 1, cc = hc & 1;

@@ -101,6 +101,8 @@ struct QkvRopeArgs {
     const float* cos_tab;   // [L, 64] fp32
     const float* sin_tab;   // [L, 64] fp32
     int L, Lpad, d_model, n_heads;
+    const int* pos_map = nullptr;  // token-cache forward: compact row r = token pos_map[r] of batch row r / Tq (k, v^T scattered to it)
+    int Tq = 0;
 };
 
 // EPI_F32 only: push the fp32 partial rows to their owners' receive buffers instead of storing them to C (tensor parallel)
@@ -124,8 +126,9 @@ void set_gemm_splitk_mode(int mode);
 
 // attention kernel selection: 4 (default, attention4.cu) or 3 (attention.cu); also MMDP_ATTN=3
 void set_attention_version(int v);
+// Lq > 0: q / out hold Lq query rows per batch row (a compact subset), k / vt the full L keys (token-cache forward)
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                  int H, int L, int Lpad, float scale, cudaStream_t stream);
+                  int H, int L, int Lpad, float scale, cudaStream_t stream, int Lq = 0);
 
 // err (nullable): device int, bit 0 is raised when an id is outside [0, vocab) (the kernel then reads row 0)
 int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, int M, int d, int64_t vocab,

@@ -172,14 +172,57 @@ class LLaDAForMultiModalGeneration:
         yield torch.empty(0, dtype=torch.bfloat16, device=self.device)
 
     def caching(self, enable: bool = True) -> None:
-        """Mirror of LLaDAModel.caching (modeling_llada.py:1415-1418). The reference's per-block K/V and logit caches only
-        change results when a caller passes `to_compute_mask` / `cat` to LLaDAModelLM.forward; no caller in the reference does
-        (the wrapper's forward cannot, modeling_xllmx_dimoo.py:41-72), so enabling the cache is output-invariant. Nothing
-        is stored here."""
+        """Mirror of LLaDAModel.caching (modeling_llada.py:1417-1421): switches the token cache on / off and drops what it holds.
+        With the cache on, `model(ids, infer=True, use_cache=True, to_compute_mask=mask, cat=key)` recomputes only the masked
+        tokens against the cached keys / values (see `forward`). The reference's own generators switch it on but never pass a
+        mask (generate_image :65-68, :127), which leaves every output unchanged - also true here."""
         self._caching = bool(enable)
+        self._cache = {}
 
     def empty_cache(self) -> None:
-        """Mirror of LLaDAModel.empty_cache (a no-op here, see caching())."""
+        """Mirror of LLaDAModel.empty_cache (modeling_llada.py:1423-1426)."""
+        self._cache = {}
+
+    def _forward_cached(self, ids: torch.Tensor, to_compute_mask: Optional[torch.Tensor], cat: str) -> torch.Tensor:
+        """Token-cache forward (modeling_llada.py:1244-1245, :929-940, :715-716, :1406-1413) on the native context: a call without a
+        mask is a full forward that (re)fills the per-block key / value caches and the logit cache of `cat`; a call with
+        `to_compute_mask [B, L]` embeds only the masked tokens, refreshes their keys / values inside the caches, attends from them
+        to ALL cached keys, and scatters their logits into the logit cache. Returns the logit cache itself, like the reference
+        (the tensor is updated in place by later calls)."""
+        B, L = ids.shape
+        Lpad = (L + 7) // 8 * 8
+        ent = self._cache.get(cat)
+        if ent is not None and ent["shape"] != (B, L):
+            raise ValueError(f"token cache '{cat}' holds a {ent['shape']} sequence, got {(B, L)}; call empty_cache() first")
+        if ent is None:
+            if to_compute_mask is not None:
+                raise ValueError(f"token cache '{cat}' is empty: run a full forward (to_compute_mask=None) before a partial one")
+            ent = {"shape": (B, L),
+                   "k": torch.empty((self.n_layers, B * L, self.d_model), dtype=torch.bfloat16, device=self.device),
+                   "vt": torch.zeros((self.n_layers, B, self.n_heads, 128, Lpad), dtype=torch.bfloat16, device=self.device),
+                   "logits": torch.empty((B, L, self.vocab_rows), dtype=torch.bfloat16, device=self.device)}
+            self._cache[cat] = ent
+        if to_compute_mask is None:
+            check(lib.mmdp_model_forward_cached(self._h, ptr(ids), B, L, L, None, ptr(ent["k"]), ptr(ent["vt"]), ptr(ent["logits"]),
+                                                stream_ptr()))
+            return ent["logits"]
+        mask = to_compute_mask.to(device=self.device, dtype=torch.bool)
+        if B != 1:
+            raise ValueError("a partial forward is single-sample: the reference indexes the rotary table with nonzero()[1] of the "
+                             "whole [B, L] mask (modeling_llada.py:715) and raises for B > 1")
+        if tuple(mask.shape) != (B, L):
+            raise ValueError("to_compute_mask must be a bool tensor of the shape of input_ids")
+        counts = mask.sum(dim=1)
+        tq = int(counts[0])
+        if tq == 0 or bool((counts != tq).any()):
+            raise ValueError("to_compute_mask must select the same non-zero number of tokens in every batch row "
+                             "(the reference reshapes the selection with .view(batch, -1))")
+        pos = mask.nonzero(as_tuple=False)[:, 1].to(torch.int32).contiguous()                       # increasing within each batch row
+        ids_c = ids[mask].contiguous()                                                               # :1244-1245
+        part = torch.empty((B * tq, self.vocab_rows), dtype=torch.bfloat16, device=self.device)
+        check(lib.mmdp_model_forward_cached(self._h, ptr(ids_c), B, L, tq, ptr(pos), ptr(ent["k"]), ptr(ent["vt"]), ptr(part), stream_ptr()))
+        ent["logits"][mask] = part                                                                   # :1409-1411
+        return ent["logits"]
 
     def raise_device_errors(self) -> None:
         """Reads and clears the sticky device-side error flags of the forwards issued so far (synchronises the stream).
@@ -204,14 +247,21 @@ class LLaDAForMultiModalGeneration:
             ids = ids.unsqueeze(0)
         return ids.contiguous()
 
-    def forward(self, input_ids=None, labels=None, infer: bool = False, use_cache: bool = False, **_) -> ModelOutput:
+    def forward(self, input_ids=None, labels=None, infer: bool = False, use_cache: bool = False, to_compute_mask=None,
+                cat: str = "", **_) -> ModelOutput:
+        """`model(input_ids, infer=True, use_cache=False).logits` of the reference wrapper (modeling_xllmx_dimoo.py:41-72). The two
+        extra keywords are those of the class underneath it, LLaDAModelLM.forward (modeling_llada.py:1475-1477): with the token
+        cache switched on (`caching(True)`) and `use_cache=True` they select the partial-recompute forward."""
         if labels is not None or not infer:
             raise NotImplementedError("only the inference branch (infer=True) is on the B200 hot path")
-        # use_cache=True: the reference then STORES K/V/logits per block (modeling_llada.py:929-940, :1406-1413) and returns the
-        # same logits - partial recompute needs `to_compute_mask`, which this call signature (like the reference wrapper's,
-        # modeling_xllmx_dimoo.py:41-72) does not have. Accepted and output-invariant; see caching().
+        if to_compute_mask is not None and not (use_cache and getattr(self, "_caching", False)):
+            raise ValueError("to_compute_mask needs the token cache: model.caching(True) and use_cache=True")
+        # use_cache=True with the cache switched on and no mask: a full forward that fills the caches (same logits);
+        # with the cache off the flag is output-invariant (the reference's stores are then never read).
         ids = self._ids_device(input_ids)
         B, L = ids.shape
+        if use_cache and getattr(self, "_caching", False):
+            return ModelOutput(logits=self._forward_cached(ids, to_compute_mask, cat), attn_key_values=None, hidden_states=None)
         logits = torch.empty((B, L, self.vocab_rows), dtype=torch.bfloat16, device=self.device)
         check(lib.mmdp_model_forward(self._h, ptr(ids), B, L, ptr(logits), None, 0, None, None, 0, 0, 0, None, stream_ptr()))
         return ModelOutput(logits=logits, attn_key_values=None, hidden_states=None)

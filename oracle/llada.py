@@ -137,3 +137,70 @@ class OracleModel:
         if ids.dim() == 1:
             ids = ids.unsqueeze(0)
         return SimpleNamespace(logits=forward_logits(ids.to(self.device), self.w, self.config))
+
+
+class CachedOracleModel:
+    """Restates the token-cache forward of the reference: LLaDAModelLM.forward(input_ids, use_cache=True, to_compute_mask=mask,
+    cat=key) after model.caching(True) - modeling_llada.py:1244-1245 (ids restricted to the masked tokens), :929-940 (per-block
+    k / v caches: stored whole without a mask, scattered at the masked positions with one), :715-716 + :412-435 (rotary with the
+    masked tokens' own positions for q, all positions for the cached k), :1406-1413 (logit cache; the cache tensor is what is
+    returned). Pinned against the real reference in oracle/make_golden_cache.py."""
+
+    def __init__(self, cfg, weights: Dict[str, torch.Tensor]):
+        self.config, self.w = cfg, weights
+        self.k, self.v, self.logit = {}, {}, {}
+
+    def empty_cache(self):
+        self.k, self.v, self.logit = {}, {}, {}
+
+    @torch.no_grad()
+    def __call__(self, input_ids, to_compute_mask=None, cat=""):
+        cfg, w = self.config, self.w
+        ids = input_ids
+        B, L = ids.shape
+        if to_compute_mask is not None:
+            assert B == 1, "the reference's rotary indexing (nonzero()[1] of the whole mask, :715) only works for batch 1"
+            ids = ids[to_compute_mask].view(B, -1)                                              # :1244-1245
+        x = F.embedding(ids, w["model.transformer.wte.weight"])
+        nh, C = cfg.n_heads, cfg.d_model
+        pos_sin, pos_cos = rotary_tables(C // nh, cfg.rope_theta, L)
+        for i in range(cfg.n_layers):
+            p = f"model.transformer.blocks.{i}."
+            T = x.shape[1]
+            xn = rms_norm(x, w[p + "attn_norm.weight"], cfg.rms_norm_eps)
+            q, k, v = (F.linear(xn, w[p + n + ".weight"]) for n in ("q_proj", "k_proj", "v_proj"))
+            key = (i, cat)
+            if key not in self.k:                                                               # :930-932
+                self.k[key] = torch.zeros(B, L, C, dtype=x.dtype)
+                self.v[key] = torch.zeros(B, L, C, dtype=x.dtype)
+            if to_compute_mask is not None:                                                     # :933-937
+                self.k[key][to_compute_mask] = k.reshape(-1, C)
+                self.v[key][to_compute_mask] = v.reshape(-1, C)
+                k, v = self.k[key], self.v[key]
+            else:                                                                               # :938-940
+                self.k[key], self.v[key] = k, v
+            qh = q.view(B, T, nh, C // nh).transpose(1, 2)
+            kh = k.view(B, L, nh, C // nh).transpose(1, 2)
+            vh = v.view(B, L, nh, C // nh).transpose(1, 2)
+            if to_compute_mask is not None:                                                     # :715-716 -> :424-429
+                qidx = to_compute_mask.nonzero(as_tuple=True)[1]
+                q_ = apply_rotary(pos_sin[:, :, qidx, :], pos_cos[:, :, qidx, :], qh.float()).type_as(qh)
+            else:
+                q_ = apply_rotary(pos_sin, pos_cos, qh.float()).type_as(qh)
+            k_ = apply_rotary(pos_sin, pos_cos, kh.float()).type_as(kh)
+            att = F.scaled_dot_product_attention(q_, k_, vh, attn_mask=None, dropout_p=0.0, is_causal=False)
+            att = att.transpose(1, 2).contiguous().view(B, T, C)
+            x = x + F.linear(att, w[p + "attn_out.weight"])
+            h = rms_norm(x, w[p + "ff_norm.weight"], cfg.rms_norm_eps)
+            h = F.silu(F.linear(h, w[p + "ff_proj.weight"])) * F.linear(h, w[p + "up_proj.weight"])
+            x = x + F.linear(h, w[p + "ff_out.weight"])
+        x = rms_norm(x, w["model.transformer.ln_f.weight"], cfg.rms_norm_eps)
+        logits = F.linear(x, w["model.transformer.ff_out.weight"])
+        if cat not in self.logit:                                                               # :1406-1413
+            self.logit[cat] = torch.zeros_like(logits)
+        if to_compute_mask is not None:
+            self.logit[cat][to_compute_mask] = logits.view(-1, logits.shape[-1])
+            logits = self.logit[cat]
+        else:
+            self.logit[cat] = logits
+        return SimpleNamespace(logits=logits)

@@ -497,3 +497,49 @@ def test_trajectory_bit_equal_to_reference_on_separated_model():
         assert txt == run["text_tokens"], run["name"]
         assert img == run["image_tokens"], run["name"]
         del model
+
+
+def test_token_cache_forward_vs_reference_golden():
+    """Token-cache forward: `model(ids, infer=True, use_cache=True, to_compute_mask=mask, cat=key)` after
+    `model.caching(True)` against the logits of the REAL reference's LLaDAModelLM.forward on the same sequence of calls (one
+    full forward, three partial ones with changed tokens, two cache keys). Floating point: the bound of the dense forward test
+    (4 bf16 ulp of the logit scale), greedy ids equal where the reference's own margin exceeds it. Also the cache semantics:
+    the returned tensor IS the logit cache, un-recomputed positions keep their logits bit for bit, and a partial forward differs
+    from the dense forward of the new ids (stale keys / values), exactly as in the reference."""
+    t = load_golden("token_cache_tiny.pt")
+    model, cfg, _ = tiny_gpu_model(t["meta"])
+    model.caching(True)
+    try:
+        for case in t["cases"]:
+            prev = None
+            for i, st in enumerate(case["steps"]):
+                out = model(st["ids"], infer=True, use_cache=True, to_compute_mask=st["mask"], cat=case["cat"]).logits
+                assert out.dtype == torch.bfloat16 and tuple(out.shape) == (1, st["ids"].shape[1], cfg.vocab_size)
+                got = out.cpu()
+                want = st["logits_cols"].float()
+                scale = want.abs().max().item()
+                tol = 4 * scale * 2.0 ** -8
+                err = (got[:, :, st["cols"]].float() - want).abs().max().item()
+                assert err <= tol, (case["name"], i, err, tol)
+                margin = (st["top2"][..., 0] - st["top2"][..., 1]).float()
+                clear = margin > 2 * tol
+                assert torch.equal(got.float().argmax(-1)[clear], st["argmax"][clear]), (case["name"], i)
+                if st["mask"] is not None:
+                    keep = ~st["mask"]
+                    assert torch.equal(got[keep], prev[keep]), "positions that were not recomputed keep their cached logits"
+                    assert out.data_ptr() == model._cache[case["cat"]]["logits"].data_ptr(), "the logit cache itself is returned"
+                prev = got.clone()
+            dense = model(case["steps"][-1]["ids"], infer=True, use_cache=False).logits.cpu()
+            assert not torch.equal(dense, prev), "a partial forward is not the dense forward of the new ids"
+        # both cache keys are alive side by side; empty_cache() drops them; a partial forward without a cache is an error
+        assert set(model._cache) == {c["cat"] for c in t["cases"]}
+        model.empty_cache()
+        st = t["cases"][0]["steps"][1]
+        with pytest.raises(ValueError):
+            model(st["ids"], infer=True, use_cache=True, to_compute_mask=st["mask"], cat="cond")
+        with pytest.raises(ValueError):
+            model(torch.cat([st["ids"], st["ids"]]), infer=True, use_cache=True, to_compute_mask=torch.cat([st["mask"], st["mask"]]), cat="x")
+    finally:
+        model.caching(False)
+    with pytest.raises(ValueError):
+        model(st["ids"], infer=True, use_cache=True, to_compute_mask=st["mask"])   # cache switched off

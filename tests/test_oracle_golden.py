@@ -236,3 +236,17 @@ def test_separated_model_trajectories_match_reference_golden():
         assert img == run["image_tokens"] and txt == run["text_tokens"], run["name"]
         for step, rec in enumerate(tr):
             assert torch.equal(rec["ids_after_text"], run["ids_after_text"][step])
+
+
+def test_token_cache_forward_matches_reference_golden(tiny):
+    """oracle.llada.CachedOracleModel == the reference's LLaDAModelLM.forward(use_cache=True, to_compute_mask, cat) after
+    caching(True) (modeling_llada.py:929-940, :1244-1245, :1406-1413): one full forward and three partial ones per cache key
+    (oracle/make_golden_cache.py)."""
+    _, cfg, sd, _ = tiny
+    t = load_golden("token_cache_tiny.pt")
+    om = llada.CachedOracleModel(cfg, sd)
+    for case in t["cases"]:
+        for st in case["steps"]:
+            lg = om(st["ids"], to_compute_mask=st["mask"], cat=case["cat"]).logits
+            assert torch.equal(lg[:, :, st["cols"]], st["logits_cols"]), case["name"]
+            assert torch.equal(lg.float().argmax(-1), st["argmax"])
