@@ -45,10 +45,6 @@ MMDP_API long long mmdp_launch_count(int reset);
  * (cta_group::1, with its split-K tail), 2 = pair kernel only for M >= 4096 and N >= 8192. Without the split-K tail the two
  * kernels are bit-identical (same K order); also settable with the environment variable MMDP_GEMM_PAIR. */
 MMDP_API void mmdp_set_gemm_pair(int on);
-/* Attention kernel generation (csrc/attention_dispatch.cu): 6 = O and P in tensor memory, 64-wide KV blocks (default);
- * 5 = same with 128-wide KV blocks; 3 = O in registers, P through shared memory. Also MMDP_ATTN=3|5|6. Same results up to
- * bf16 rounding of P. */
-MMDP_API void mmdp_set_attention_version(int v);
 /* Split-K tail of the persistent GEMM (csrc/gemm.cu): 0 = never, 1 = residual epilogues only, 2 (default) = every epilogue
  * where the launch planner's cost model says it pays, 3 = whenever a partial last wave exists (tests).
  * The tiles of a partial last wave are split along K over the idle SMs; partial sums meet in an fp32 workspace owned per

@@ -63,7 +63,6 @@ SIGNATURES = {
     "mmdp_prof_summary": (_i, [_vp, _vp, _vp]),
     "mmdp_launch_count": (C.c_longlong, [_i]),
     "mmdp_set_gemm_pair": (None, [_i]),
-    "mmdp_set_attention_version": (None, [_i]),
     "mmdp_set_gemm_splitk": (None, [_i]),
     "mmdp_set_pdl": (None, [_i]),
     "mmdp_set_option": (_i, [C.c_char_p, _i]),

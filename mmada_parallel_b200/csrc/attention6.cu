@@ -1,5 +1,6 @@
 // Attention forward v6 (default): softmax(Q K^T / sqrt(128)) V for head_dim 128, no mask, whole-sequence KV.
-// Same math / layouts / interface as attention.cu (v3); restructured around tensor memory after three ncu passes
+// The third generation of this kernel (earlier ones kept O in registers and passed P through shared memory); restructured
+// around tensor memory after three ncu passes
 // (profiles/r01/README.md):
 //   * one CTA = one 128-row query tile of one head; KV blocks of 64; 7 warps: 4 softmax (thread = query row), K producer,
 //     MMA issuer, V^T producer; TWO CTAs per SM (112 KB smem, 256 TMEM columns, 107 registers each) so that one CTA's

@@ -1,4 +1,4 @@
-// Softmax arithmetic shared by the attention kernels with TMEM-resident O (attention5.cu, attention6.cu).
+// Softmax arithmetic of the attention kernel (attention6.cu).
 //
 // The softmax warps of those kernels are instruction-issue bound (ncu, profiles/r01/README.md: no pipe above 45 %, ~40 %
 // of the samples are dependency waits), so the per-element instruction count is what matters:
@@ -37,7 +37,7 @@ __device__ __forceinline__ float ex2_mufu(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float ex2_poly(float x) {  // see attention.cu::ex2_fma
+__device__ __forceinline__ float ex2_poly(float x) {  // 2^x on the FMA pipe: Cody-Waite split (magic-number rounding) + cubic on [-0.5, 0.5]
     x = fmaxf(x, -126.0f);
     const float t = x + 12582912.0f;
     const float f = x - (t - 12582912.0f);

@@ -124,8 +124,6 @@ void set_gemm_pair_mode(int on);
 int gemm_splitk_mode();
 void set_gemm_splitk_mode(int mode);
 
-// attention kernel selection: 4 (default, attention4.cu) or 3 (attention.cu); also MMDP_ATTN=3
-void set_attention_version(int v);
 // Lq > 0: q / out hold Lq query rows per batch row (a compact subset), k / vt the full L keys (token-cache forward)
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                   int H, int L, int Lpad, float scale, cudaStream_t stream, int Lq = 0);

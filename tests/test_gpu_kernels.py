@@ -167,14 +167,13 @@ def test_qkv_rope_and_attention(B, L, H):
     assert_attention_close(o, o_ref, f"attention B{B} L{L} H{H}")
 
 
-@pytest.mark.parametrize("version", [6, 5, 3])
-def test_attention_versions_and_lazy_rescale(version):
-    """Every attention kernel generation (csrc/attention_dispatch.cu) against the fp32 reference, on random scores and on
+def test_attention_lazy_rescale():
+    """The attention kernel against the fp32 reference, on random scores and on
     scores whose magnitude grows along the KV axis, so that the running row max jumps by far more than the lazy-rescale
     threshold (2^8) in many KV blocks - the path that rescales the TMEM-resident O accumulator."""
     from mmada_parallel_b200 import _lib
     scale = 1.0 / math.sqrt(128.0)
-    _lib.lib.mmdp_set_attention_version(version)
+    version = 6
     try:
         for B, L, H, grow in [(2, 333, 2, 0.0), (1, 1000, 2, 60.0), (1, 129, 1, 200.0)]:
             torch.manual_seed(version * 100 + L)
@@ -193,11 +192,10 @@ def test_attention_versions_and_lazy_rescale(version):
             o_ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1) @ vh).transpose(1, 2).reshape(M, d)
             assert_attention_close(o, o_ref, f"attention v{version} L{L} grow{grow}")
     finally:
-        _lib.lib.mmdp_set_attention_version(6)
+        pass
 
 
-@pytest.mark.parametrize("version", [6, 5, 3])
-def test_attention_bitwise_repeatable(version):
+def test_attention_bitwise_repeatable():
     """The same attention launch repeated many times at the full sequence length must be bitwise identical. (A parity wait
     that could return two mbarrier phases early made v6 read O before the last PV MMAs retired - rare, timing dependent,
     a few query rows per launch; this is the stress that exposes such races.) Two co-resident CTAs per SM, B=2."""
@@ -209,7 +207,6 @@ def test_attention_bitwise_repeatable(version):
     k = bf(torch.randn(M, d, device="cuda"))
     vt = torch.zeros(B, H, 128, Lpad, dtype=torch.bfloat16, device="cuda")
     vt[..., :L] = bf(torch.randn(B, H, 128, L, device="cuda"))
-    _lib.lib.mmdp_set_attention_version(version)
     try:
         ref = _lib.attention(q, k, vt, B, H, L, 1.0 / math.sqrt(128.0)).clone()
         bad = 0
@@ -217,7 +214,7 @@ def test_attention_bitwise_repeatable(version):
             bad += int(not torch.equal(_lib.attention(q, k, vt, B, H, L, 1.0 / math.sqrt(128.0)), ref))
         assert bad == 0, f"{bad} of 150 launches differ"
     finally:
-        _lib.lib.mmdp_set_attention_version(6)
+        pass
 
 
 def test_rmsnorm_embed_lfq():

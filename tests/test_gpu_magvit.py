@@ -1,8 +1,12 @@
 """MAGVITv2.decode_code on the B200 (TF32 tcgen05 convolutions) against the golden images produced by the REAL
 reference decoder (fp32, CPU; oracle pinned bit-exact in oracle/make_golden_magvit.py).
 Floating-point tolerance (stated): TF32 products (10-bit mantissa) through ~35 convolutions with GroupNorm in between;
-per-pixel |err| <= 0.08 and mean |err| <= 0.01 on images with std ~0.55, |max| ~3.4 (on average inside one 8-bit pixel
-step after the caller's (x+1)/2 mapping)."""
+per-pixel |err| <= 0.02 and mean |err| <= 0.003 on images with std ~0.55, |max| ~3.4 (measured on the B200: max 0.0078,
+mean 0.0013 - well inside one 8-bit pixel step, 1/127.5 = 0.0078 after the caller's (x+1)/2 mapping).
+Deviation from torch's defaults, stated: every contraction of the decoder runs with TF32 products, including the two
+matmuls of the mid-block AttnBlock; torch.backends.cuda.matmul.allow_tf32 defaults to False (fp32 matmul) while cuDNN
+convolutions default to TF32, so the reference on a GPU would run those two matmuls in fp32 - 2 of ~60 contractions,
+inside the bound above."""
 import pytest
 import torch
 
@@ -29,7 +33,7 @@ def test_decode_code_vs_reference_golden(tag):
     err = (got - g["image"]).abs()
     print(f"[magvit {tag}] max err {err.max():.4f} mean err {err.mean():.5f} (image std {g['std']:.3f})")
     assert torch.isfinite(out).all()
-    assert err.max() <= 0.08 and err.mean() <= 0.01
+    assert err.max() <= 0.02 and err.mean() <= 0.003
     assert abs(float(out.mean()) - g["mean"]) < 5e-3 and abs(float(out.std()) - g["std"]) < 5e-3
     # determinism + batch independence
     out2 = m.decode_code(idx)

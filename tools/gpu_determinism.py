@@ -26,7 +26,6 @@ L = 2414
 ids = torch.randint(0, 126000, (2, L), device="cuda", generator=g)
 rows = torch.cat([torch.arange(2157, 2413), torch.arange(L + 1100, L + 1100 + 64)]).to(torch.int32).cuda()
 for ver in [int(v) for v in os.environ.get('MMDP_DET_VERS', '6,3').split(',')]:
-    _lib.lib.mmdp_set_attention_version(ver)
     ref, _ = m.forward_rows(ids, rows_a=rows)
     ref = ref.clone()
     hid = m.hidden_state().clone() if hasattr(m, "hidden_state") else None
