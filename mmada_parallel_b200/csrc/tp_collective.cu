@@ -73,6 +73,10 @@ template <int NV>  // d <= 2048 * NV columns (d % 8 == 0): every thread owns up 
 __global__ void __launch_bounds__(kTpThreads) tp_reduce_norm_kernel(TpReduceArgs a) {
     const int tid = threadIdx.x;
     uint32_t* flags_local = a.flags[a.my_rank];
+    // programmatic dependent launch: this grid may start under the tail of the GEMM that pushes this rank's partial rows; the
+    // "my pushes are complete" signal below must not be sent before that GEMM has completed
+    pdl_launch_dependents();
+    pdl_wait();
     // phase 0: tell every rank that this rank has reached this collective - its partial sums are complete and it no longer
     // reads the activation buffer the peers are about to overwrite - then wait for everybody's
     if (blockIdx.x == 0 && tid < a.n_ranks) st_release_sys(a.flags[tid] + 0 * kTpMaxRanks + a.my_rank, a.epoch);
@@ -165,6 +169,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_norm_kernel(TpReduceArgs
 }
 
 __global__ void tp_wait_kernel(const uint32_t* flags_local, int phase, int n_ranks, uint32_t epoch) {
+    pdl_launch_dependents();
+    pdl_wait();
     tp_wait_flags(flags_local, phase, n_ranks, epoch);
 }
 
@@ -188,17 +194,18 @@ int tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16
     a.row0 = row0; a.nrows = nrows; a.d = d; a.eps = eps; a.epoch = epoch; a.done_counter = done_counter;
     // bytes this rank moves: reads n_src fp32 rows + x, writes x + n_ranks bf16 rows
     LaunchScope ls(LK_ROW, (double)nrows * d * (4.0 * n_src + 4.0 + 2.0 * n_ranks), stream);
+    const bool pdl = pdl_mode() != 0;
+    cudaError_t e;
     switch ((d + 2047) / 2048) {
-        case 1: tp_reduce_norm_kernel<1><<<nrows, kTpThreads, 0, stream>>>(a); break;
-        case 2: tp_reduce_norm_kernel<2><<<nrows, kTpThreads, 0, stream>>>(a); break;
-        case 3: tp_reduce_norm_kernel<3><<<nrows, kTpThreads, 0, stream>>>(a); break;
-        default: tp_reduce_norm_kernel<4><<<nrows, kTpThreads, 0, stream>>>(a); break;
+        case 1: e = launch_ex(tp_reduce_norm_kernel<1>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
+        case 2: e = launch_ex(tp_reduce_norm_kernel<2>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
+        case 3: e = launch_ex(tp_reduce_norm_kernel<3>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
+        default: e = launch_ex(tp_reduce_norm_kernel<4>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
     }
-    MMDP_CUDA(cudaGetLastError());
+    MMDP_CUDA(e);
     // the consumer of xn (the next column-parallel GEMM) needs every rank's rows: wait for phase 1 of all ranks
     LaunchScope ls2(LK_ROW, 0.0, stream);
-    tp_wait_kernel<<<1, 32, 0, stream>>>(flags[my_rank], 1, n_ranks, epoch);
-    MMDP_CUDA(cudaGetLastError());
+    MMDP_CUDA(launch_ex(tp_wait_kernel, dim3(1), dim3(32), 0, stream, pdl, false, (const uint32_t*)flags[my_rank], 1, n_ranks, epoch));
     return 0;
 }
 
