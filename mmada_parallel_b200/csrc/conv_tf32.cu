@@ -218,9 +218,12 @@ int conv_tf32(const float* A, int lda, long long a_rows, const float* W, int M, 
 // GroupNorm(32 groups) statistics over the interior pixels of padded NHWC images. grid (chunks, B); thread layout:
 // TC = min(C, 256) lanes along channels (coalesced), 256/TC lanes along pixels; fp64 accumulation across CTAs.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int C, int H, int W, double* __restrict__ stats) {
-    const int b = blockIdx.y, Wp = W + 2, cpg = C / 32;
-    const float* xb = x + (size_t)b * (H + 2) * Wp * C;
-    const int TC = C < 256 ? C : 256, PP = 256 / TC;
+    // per-(image, group) sum and sum of squares of the interior pixels. A thread owns four consecutive channels (one float4) and
+    // walks the CTA's pixel chunk with 256 / (C/4) pixel lanes, four independent loads in flight (the first version - one
+    // scalar load per thread and iteration, 256 CTAs - ran at 0.5 TB/s on the 134 MB full-resolution tensors: latency-bound)
+    const int b = blockIdx.y, Wp = W + 2, cpg = C / 32, C4 = C / 4;
+    const float4* xb = reinterpret_cast<const float4*>(x + (size_t)b * (H + 2) * Wp * C);
+    const int TC = C4 < 256 ? C4 : 256, PP = 256 / TC;
     const int cl = threadIdx.x % TC, pl = threadIdx.x / TC;
     const long long npix = (long long)H * W;
     const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
@@ -230,16 +233,32 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
     __syncthreads();
     if (pl < PP) {
-        for (int ch = cl; ch < C; ch += TC) {
-            float s = 0.f, q = 0.f;
-            for (long long pp = p0 + pl; pp < p1; pp += PP) {
-                const int y = (int)(pp / W), xx = (int)(pp - (long long)y * W);
-                const float v = xb[((size_t)(y + 1) * Wp + xx + 1) * C + ch];
-                s += v;
-                q = fmaf(v, v, q);
+        for (int c4 = cl; c4 < C4; c4 += TC) {
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+            for (long long pp = p0 + pl; pp < p1; pp += 4LL * PP) {
+                float4 v[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const long long pt = pp + (long long)t * PP;
+                    if (pt < p1) {
+                        const int y = (int)(pt / W), xx = (int)(pt - (long long)y * W);
+                        v[t] = xb[((size_t)(y + 1) * Wp + xx + 1) * C4 + c4];
+                    } else {
+                        v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s[0] += v[t].x; s[1] += v[t].y; s[2] += v[t].z; s[3] += v[t].w;
+                    q[0] = fmaf(v[t].x, v[t].x, q[0]); q[1] = fmaf(v[t].y, v[t].y, q[1]);
+                    q[2] = fmaf(v[t].z, v[t].z, q[2]); q[3] = fmaf(v[t].w, v[t].w, q[3]);
+                }
             }
-            atomicAdd(&s_sum[ch / cpg], (double)s);
-            atomicAdd(&s_sq[ch / cpg], (double)q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                atomicAdd(&s_sum[(c4 * 4 + k) / cpg], (double)s[k]);
+                atomicAdd(&s_sq[(c4 * 4 + k) / cpg], (double)q[k]);
+            }
         }
     }
     __syncthreads();
@@ -429,8 +448,8 @@ int gn_swish(const float* x, float* y, int B, int C, int H, int W, double* stats
     if (C % 32) return set_error("group_norm: channels must be a multiple of 32");
     MMDP_CUDA(cudaMemsetAsync(stats_ws, 0, (size_t)B * 32 * 2 * sizeof(double), stream));
     const long long npix = (long long)H * W;
-    int chunks = (int)((npix + 1023) / 1024);
-    if (chunks > 1024) chunks = 1024;
+    int chunks = (int)((npix + 127) / 128);
+    if (chunks > 148 * 16) chunks = 148 * 16;
     {
         LaunchScope ls(LK_ROW, (double)B * npix * C * 4, stream);
         gn_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, C, H, W, stats_ws);
