@@ -445,7 +445,7 @@ def measure_variant_m(args, rank: int, world: int, device: str, steps: int, warm
     if prof is not None:
         peaks = load_peaks()
         gm, gf, gn = prof["gemm"]
-        rec["roofline"] = {"kernel": "gemm_bf16_kernel (tcgen05, all epilogues)", "bound": "tensor", "achieved": gf / (gm / 1e3) / 1e12 if gm else None,
+        rec["roofline"] = {"kernel": "gemm_pair_kernel / gemm_bf16_kernel (tcgen05, all epilogues)", "bound": "tensor", "achieved": gf / (gm / 1e3) / 1e12 if gm else None,
                            "peak": peaks[0], "unit": "TFLOP/s", "frac": (gf / (gm / 1e3) / 1e12 / peaks[0]) if gm else None, "peak_source": peaks[1],
                            "launches": gn, "avg_launch_ms": gm / max(1, gn)}
         rec["kernel_breakdown_one_sample_ms"] = {"gemm": gm, "attention": prof["attention"][0], "row_kernels": prof["row"][0], "sampling": prof["sampling"][0],
@@ -766,7 +766,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clock_info,
-        "roofline": {"kernel": "gemm_bf16_kernel (tcgen05, all epilogues)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+        "roofline": {"kernel": "gemm_pair_kernel / gemm_bf16_kernel (tcgen05 cta_group::2 / ::1, all epilogues)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
                      "peak_source": peak_src, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(1, gemm_n),
                      "algorithmic_flops_per_launch": gemm_flops / max(1, gemm_n)},
