@@ -92,6 +92,35 @@ MMDP_API int mmdp_tp_reduce_norm(const float* recv_local, int rows_per_rank, int
                         int n_ranks, int my_rank, uint16_t* x_shard, const uint16_t* weight, int row0, int nrows, int d, float eps,
                         uint32_t epoch, uint32_t* done_counter, void* stream);
 
+/* The whole tensor-parallel body in one call (the per-layer sequence TensorParallelLLaDA used to issue from Python: ~10 launches
+ * per layer left a TP=8 rank CPU-bound): embedding of this rank's rows, norm + broadcast, then per layer column-parallel QKV+RoPE,
+ * attention on the local heads, row-parallel attn_out pushed to the owners, reduce + residual + ff_norm + broadcast, column-parallel
+ * gate/up + SwiGLU, row-parallel ff_out pushed, reduce + residual + next norm (ln_f after the last layer) + broadcast.
+ * On return (stream order) every rank's xn buffer holds ln_f(x) for all B*L rows. Pointers are device pointers owned by the caller. */
+typedef struct mmdp_tp_layer {
+    const uint16_t* wqkv;       /* [3 * d_attn, d]  q | k | v rows of the local heads */
+    const uint16_t* wo;         /* [d, d_attn] */
+    const uint16_t* w13;        /* [2 * ff_local, d] gate / up interleaved in 128-row blocks */
+    const uint16_t* w2;         /* [d, ff_local] */
+    const uint16_t* attn_norm;  /* [d] */
+    const uint16_t* ff_norm;    /* [d] */
+} mmdp_tp_layer;
+typedef struct mmdp_tp_ctx {
+    int32_t d_model, n_heads_local, ff_local, n_layers, n_ranks, rank;
+    float rms_eps;
+    const mmdp_tp_layer* layers;                 /* HOST array [n_layers] */
+    const uint16_t* wte; const uint16_t* ln_f; int64_t vocab;
+    const float* cos_tab; const float* sin_tab;  /* [max_seq_len, 64] */
+    uint16_t *q, *k, *att, *h, *vt;              /* work buffers: [M, d_attn] x3, [M, ff_local], [B, H_local, 128, Lpad] (pad columns zero) */
+    uint16_t* x_shard;                           /* [rows_per_rank, d] */
+    float* const* recv[2];                       /* HOST arrays [n_ranks] of the two receive buffers of every rank */
+    uint16_t* const* xn;                         /* HOST array [n_ranks] of the activation buffers */
+    uint32_t* const* flags;                      /* HOST array [n_ranks] of the flag arrays */
+    uint32_t* done_counter;
+} mmdp_tp_ctx;
+/* epoch0: the last epoch used so far; the call uses epoch0 + 1 ... epoch0 + 2 * n_layers + 1 (returned through *epoch_out). */
+MMDP_API int mmdp_tp_forward(const mmdp_tp_ctx* c, const int64_t* ids, int B, int L, uint32_t epoch0, uint32_t* epoch_out, void* stream);
+
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */
 #define MMDP_EPI_PLAIN 0   /* C = bf16(A W^T)                                 nn.Linear, modeling_llada.py:1402      */
 #define MMDP_EPI_RESID 1   /* C = bf16(bf16(A W^T) + R)                       attn_out :744 + :953; ff_out :968+:970  */

@@ -42,6 +42,19 @@ class VqDecConfig(C.Structure):
                 ("latent_w", C.c_int32)]
 
 
+class TpLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wo", "w13", "w2", "attn_norm", "ff_norm")]
+
+
+class TpCtx(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("n_heads_local", C.c_int32), ("ff_local", C.c_int32), ("n_layers", C.c_int32),
+                ("n_ranks", C.c_int32), ("rank", C.c_int32), ("rms_eps", C.c_float), ("layers", C.POINTER(TpLayer)),
+                ("wte", C.c_void_p), ("ln_f", C.c_void_p), ("vocab", C.c_int64), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
+                ("q", C.c_void_p), ("k", C.c_void_p), ("att", C.c_void_p), ("h", C.c_void_p), ("vt", C.c_void_p),
+                ("x_shard", C.c_void_p), ("recv", C.POINTER(C.c_void_p) * 2), ("xn", C.POINTER(C.c_void_p)),
+                ("flags", C.POINTER(C.c_void_p)), ("done_counter", C.c_void_p)]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [
         ("d_model", C.c_int32),
@@ -71,6 +84,7 @@ SIGNATURES = {
     "mmdp_ipc_export": (_i, [_vp, _vp]),
     "mmdp_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
     "mmdp_ipc_close": (_i, [_vp]),
+    "mmdp_tp_forward": (_i, [C.POINTER(TpCtx), _vp, _i, _i, C.c_uint32, C.POINTER(C.c_uint32), _vp]),
     "mmdp_gemm_f32_scatter": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "mmdp_tp_reduce_norm": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _f, C.c_uint32, _vp, _vp]),
     "mmdp_gemm_bf16": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),

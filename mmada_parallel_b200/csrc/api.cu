@@ -210,6 +210,42 @@ MMDP_API int mmdp_gemm_f32_scatter(const uint16_t* A, int lda, const uint16_t* W
     return gemm_bf16(EPI_F32, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, nullptr, N, nullptr, 0, nullptr, (cudaStream_t)stream, &sc);
 }
 
+MMDP_API int mmdp_tp_forward(const mmdp_tp_ctx* c, const int64_t* ids, int B, int L, uint32_t epoch0, uint32_t* epoch_out, void* stream) {
+    if (!c || !ids || !epoch_out) return set_error("mmdp_tp_forward: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int d = c->d_model, Hl = c->n_heads_local, da = Hl * 128, ffl = c->ff_local, tp = c->n_ranks;
+    const int M = B * L, Lpad = ((L + 7) / 8) * 8;
+    const int R = (M + tp - 1) / tp, row0 = c->rank * R, nrows = (M - row0 < R ? M - row0 : R);
+    if (nrows < 1 || M - (tp - 1) * R < 1) return set_error("mmdp_tp_forward: %d tokens cannot be split over %d ranks with at least one row each", M, tp);
+    const float scale = 1.0f / sqrtf(128.0f);
+    uint32_t epoch = epoch0;
+    GemmScatter sc[2]{};
+    for (int b = 0; b < 2; ++b) {
+        for (int r = 0; r < tp; ++r) sc[b].dst[r] = c->recv[b][r];
+        sc[b].rows_per_rank = R; sc[b].slot = c->rank;
+    }
+    auto reduce = [&](int buf, const uint16_t* w) -> int {
+        return tp_reduce_norm(buf >= 0 ? c->recv[buf][c->rank] : nullptr, R, buf >= 0 ? tp : 0, c->xn, c->flags, tp, c->rank, c->x_shard, w, row0, nrows, d,
+                              c->rms_eps, ++epoch, c->done_counter, s);
+    };
+    const bf16* xn = (const bf16*)c->xn[c->rank];
+    if (embed_rows(ids + row0, (const bf16*)c->wte, (bf16*)c->x_shard, nrows, d, c->vocab, s, nullptr)) return -1;
+    if (reduce(-1, c->layers[0].attn_norm)) return -1;
+    QkvRopeArgs qa{(bf16*)c->q, (bf16*)c->k, (bf16*)c->vt, c->cos_tab, c->sin_tab, L, Lpad, da, Hl};
+    for (int li = 0; li < c->n_layers; ++li) {
+        const mmdp_tp_layer& l = c->layers[li];
+        if (gemm_bf16(EPI_QKVROPE, xn, d, (const bf16*)l.wqkv, d, M, 3 * da, d, nullptr, 0, nullptr, 0, &qa, s)) return -1;
+        if (attention_fwd((const bf16*)c->q, (const bf16*)c->k, (const bf16*)c->vt, (bf16*)c->att, B, Hl, L, Lpad, scale, s)) return -1;
+        if (gemm_bf16(EPI_F32, (const bf16*)c->att, da, (const bf16*)l.wo, da, M, d, da, nullptr, d, nullptr, 0, nullptr, s, &sc[0])) return -1;
+        if (reduce(0, l.ff_norm)) return -1;
+        if (gemm_bf16(EPI_SWIGLU, xn, d, (const bf16*)l.w13, d, M, 2 * ffl, d, (bf16*)c->h, ffl, nullptr, 0, nullptr, s)) return -1;
+        if (gemm_bf16(EPI_F32, (const bf16*)c->h, ffl, (const bf16*)l.w2, ffl, M, d, ffl, nullptr, d, nullptr, 0, nullptr, s, &sc[1])) return -1;
+        if (reduce(1, li + 1 < c->n_layers ? c->layers[li + 1].attn_norm : c->ln_f)) return -1;
+    }
+    *epoch_out = epoch;
+    return 0;
+}
+
 MMDP_API void mmdp_prof_enable(int on) { prof_enable(on); }
 MMDP_API int mmdp_prof_summary(double* ms, double* work, long long* launches) { return prof_summary(ms, work, launches); }
 MMDP_API long long mmdp_launch_count(int reset) { return launch_count(reset); }

@@ -206,54 +206,57 @@ class TensorParallelLLaDA:
         out.view(n, self.tp, c).copy_(buf.permute(1, 0, 2))
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _reduce_norm(self, recv_idx: Optional[int], weight: torch.Tensor, M: int):
-        """Sum of the fp32 partial rows the ranks pushed into receive buffer `recv_idx` (None: no partials), residual add on
-        this rank's rows, RMSNorm with `weight`, result into every rank's xn; on return (in stream order) all M rows of
-        self.xn are valid."""
-        self._epoch += 1
-        r0, nrows = row_partition(M, self.tp, self.rank)
-        recv = self._recv[recv_idx].own if recv_idx is not None else None
-        check(lib.mmdp_tp_reduce_norm(recv, rows_per_rank(M, self.tp), self.tp if recv_idx is not None else 0, self._xn.array,
-                                      self._flags.array, self.tp, self.rank, ptr(self.x), ptr(weight), r0, nrows, self.d_model,
-                                      self.rms_eps, self._epoch, ptr(self._done), stream_ptr()))
-
-    def _row_parallel_gemm(self, a: torch.Tensor, wt: torch.Tensor, K: int, M: int, recv_idx: int):
-        """fp32 partial sums of a row-parallel linear: pushed to the owners (p2p) or stored locally for the NCCL all-reduce."""
-        d, s = self.d_model, stream_ptr()
-        if self.collective == "p2p":
-            check(lib.mmdp_gemm_f32_scatter(ptr(a), K, ptr(wt), K, M, d, K, self._recv[recv_idx].array, self.tp,
-                                            rows_per_rank(M, self.tp), self.rank, s))
-        else:
-            check(lib.mmdp_gemm_bf16(EPI_F32, ptr(a), K, ptr(wt), K, M, d, K, ptr(self.part), d, None, 0, s))
-
-    def _layers(self, B: int, L: int, M: int, Lpad: int):
+    def _layers_nccl(self, B: int, L: int, M: int, Lpad: int):
+        """Round 1's formulation, kept as the measured baseline (`collective="nccl"`): fp32 partial sums stored locally,
+        `dist.all_reduce` between the kernels, then the residual add and the RMSNorm as separate launches."""
         d, s, w = self.d_model, stream_ptr(), self.w
         scale = 1.0 / math.sqrt(128.0)
-        p2p = self.collective == "p2p"
         x, xn = self.x, self.xn
         for i in range(self.n_layers):
             p = f"blocks.{i}."
-            if not p2p:
-                check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "attn_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
+            check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "attn_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
             check(lib.mmdp_qkv_rope_tp(ptr(xn), d, ptr(w[p + "wqkv"]), M, d, self.h_local, L, Lpad, ptr(self.cos), ptr(self.sin),
                                        ptr(self.q), ptr(self.k), ptr(self.vt), s))
             check(lib.mmdp_attention(ptr(self.q), ptr(self.k), ptr(self.vt), ptr(self.att), B, self.h_local, L, Lpad, scale, s))
-            self._row_parallel_gemm(self.att, w[p + "wo"], self.d_attn, M, 0)
-            if p2p:
-                self._reduce_norm(0, w[p + "ff_norm"], M)
-            else:
-                self._allreduce(self.part[:M])
-                check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(self.part), d, M, d, s))
-                check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "ff_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
+            check(lib.mmdp_gemm_bf16(EPI_F32, ptr(self.att), self.d_attn, ptr(w[p + "wo"]), self.d_attn, M, d, self.d_attn,
+                                     ptr(self.part), d, None, 0, s))
+            self._allreduce(self.part[:M])
+            check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(self.part), d, M, d, s))
+            check(lib.mmdp_rmsnorm(ptr(x), d, None, ptr(w[p + "ff_norm"]), ptr(xn), d, M, d, self.rms_eps, s))
             check(lib.mmdp_gemm_bf16(EPI_SWIGLU, ptr(xn), d, ptr(w[p + "w13"]), d, M, 2 * self.ff_local, d, ptr(self.h),
                                      self.ff_local, None, 0, s))
-            self._row_parallel_gemm(self.h, w[p + "w2"], self.ff_local, M, 1)
-            if p2p:
-                nxt = w[f"blocks.{i + 1}.attn_norm"] if i + 1 < self.n_layers else w["ln_f"]
-                self._reduce_norm(1, nxt, M)
-            else:
-                self._allreduce(self.part[:M])
-                check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(self.part), d, M, d, s))
+            check(lib.mmdp_gemm_bf16(EPI_F32, ptr(self.h), self.ff_local, ptr(w[p + "w2"]), self.ff_local, M, d, self.ff_local,
+                                     ptr(self.part), d, None, 0, s))
+            self._allreduce(self.part[:M])
+            check(lib.mmdp_resid_add_f32(ptr(x), d, ptr(self.part), d, M, d, s))
+
+    def _native_ctx(self, B: int, L: int):
+        """The C-side description of this rank (mmdp_tp_ctx): built once per (B, L) - the V^T buffer depends on it."""
+        key = (B, L)
+        if getattr(self, "_ctx_key", None) == key:
+            return self._ctx
+        w = self.w
+        layers = (_lib.TpLayer * self.n_layers)()
+        for i in range(self.n_layers):
+            p = f"blocks.{i}."
+            for name, t in (("wqkv", w[p + "wqkv"]), ("wo", w[p + "wo"]), ("w13", w[p + "w13"]), ("w2", w[p + "w2"]),
+                            ("attn_norm", w[p + "attn_norm"]), ("ff_norm", w[p + "ff_norm"])):
+                setattr(layers[i], name, t.data_ptr())
+        c = _lib.TpCtx()
+        c.d_model, c.n_heads_local, c.ff_local, c.n_layers, c.n_ranks, c.rank = self.d_model, self.h_local, self.ff_local, self.n_layers, self.tp, self.rank
+        c.rms_eps = self.rms_eps
+        c.layers = layers
+        c.wte, c.ln_f, c.vocab = w["wte"].data_ptr(), w["ln_f"].data_ptr(), w["wte"].shape[0]
+        c.cos_tab, c.sin_tab = self.cos.data_ptr(), self.sin.data_ptr()
+        c.q, c.k, c.att, c.h, c.vt = self.q.data_ptr(), self.k.data_ptr(), self.att.data_ptr(), self.h.data_ptr(), self.vt.data_ptr()
+        c.x_shard = self.x.data_ptr()
+        c.recv[0] = C.cast(self._recv[0].array, C.POINTER(C.c_void_p))
+        c.recv[1] = C.cast(self._recv[1].array, C.POINTER(C.c_void_p))
+        c.xn = C.cast(self._xn.array, C.POINTER(C.c_void_p))
+        c.flags = C.cast(self._flags.array, C.POINTER(C.c_void_p))
+        c.done_counter = self._done.data_ptr()
+        self._ctx, self._ctx_layers, self._ctx_key = c, layers, key   # (keep the layer array alive)
+        return c
 
     def _final_norm(self, ids: torch.Tensor) -> torch.Tensor:
         """Runs embedding + all blocks; returns ln_f(x) for ALL rows [M, d] (p2p) or the raw residual stream x (nccl)."""
@@ -269,13 +272,14 @@ class TensorParallelLLaDA:
         if self.collective == "p2p":
             if row_partition(M, self.tp, self.tp - 1)[1] < 1:
                 raise _lib.MmdpError(f"TensorParallelLLaDA: {M} tokens cannot be split over {self.tp} ranks with at least one row each")
-            r0, nrows = row_partition(M, self.tp, self.rank)
-            check(lib.mmdp_embed(ids.data_ptr() + r0 * 8, ptr(wte), ptr(self.x), nrows, d, wte.shape[0], s))   # this rank's rows only
-            self._reduce_norm(None, self.w["blocks.0.attn_norm"], M)
-        else:
-            check(lib.mmdp_embed(ptr(ids), ptr(wte), ptr(self.x), M, d, wte.shape[0], s))
-        self._layers(B, L, M, Lpad)
-        return self.xn if self.collective == "p2p" else self.x
+            # the whole body is one native call (a Python loop of ~10 launches per layer left a TP=8 rank CPU-bound)
+            out = C.c_uint32(0)
+            check(lib.mmdp_tp_forward(C.byref(self._native_ctx(B, L)), ptr(ids), B, L, self._epoch, C.byref(out), s))
+            self._epoch = int(out.value)
+            return self.xn
+        check(lib.mmdp_embed(ptr(ids), ptr(wte), ptr(self.x), M, d, wte.shape[0], s))
+        self._layers_nccl(B, L, M, Lpad)
+        return self.x
 
     @torch.no_grad()
     def forward_rows(self, ids: torch.Tensor, rows_a: Optional[torch.Tensor] = None, rows_b: Optional[torch.Tensor] = None,
