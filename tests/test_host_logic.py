@@ -174,3 +174,19 @@ def test_tensor_parallel_row_partition():
                 assert 0 <= n <= R
                 assert all(row // R == r for row in (r0, r0 + n - 1)) if n else True
     assert row_partition(2414, 8, 7) == (2114, 300)
+
+
+def test_bench_workload_shapes_and_counts():
+    """bench.py's synthetic input A is the SURVEY 8d layout (L = P + 2374 = 2414, image_start 1100, text span [2157, 2413)) and its
+    FLOP count is the minimal-equivalent figure of BASELINE.md section 3 (7.101 PFLOP per sample); the CPU-arm protocol reports the
+    host it ran on."""
+    import bench
+    lay = bench.synthetic_layout(seed=0)
+    assert lay["input_ids"].shape == (1, 2414)
+    assert (lay["image_start"], lay["text_start"], lay["text_end"]) == (1100, 2157, 2413)
+    assert lay["uncon_text"].shape[1] == 1061 and lay["uncon_image"].shape[1] == 40
+    assert int((lay["input_ids"] == bench.MASK).sum()) == 1024 + 256
+    assert abs(bench.algorithmic_flops_per_sample(bench.MODEL_8B) / 1e15 - 7.101) < 0.002
+    info = bench.host_cpu_info()
+    assert 1 <= info["physical_cores"] <= info["logical_cpus"] and isinstance(info["model"], str)
+    assert bench.load_peaks()[0] > 100
