@@ -569,6 +569,14 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
         dist.barrier()
         torch.cuda.synchronize()
         ms = max_over_ranks(e0.elapsed_time(e1), device=device)
+        # where the tensor-parallel sample spends its time (rank 0's launches bracketed by CUDA events; every rank runs the pass
+        # because the forward contains the cross-rank flags). "row" = reduce + residual + norm + broadcast kernels incl. their
+        # waits for the peers, "gemm" includes the fused reduce-scatter pushes.
+        _lib.lib.mmdp_prof_enable(1)
+        denoise_loop(new_state(), generator=rng, **loop_kw)
+        tp_prof = _lib.prof_summary()
+        _lib.lib.mmdp_prof_enable(0)
+        dist.barrier()
         # ranks in lock-step: every rank's final id buffer equals rank 0's
         mine = final[0].clone()
         ref = mine.clone()
@@ -600,7 +608,9 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
         nccl_tok_s = f"error: {type(e).__name__}: {e}"[:200]
     v = steps * TOKENS_PER_SAMPLE / (ms / 1e3)
     return {"metric": "denoised_tokens_per_sec", "value": v, "nccl_allreduce_baseline_tokens_per_s": nccl_tok_s,
-            "collective": "fused reduce + residual + RMSNorm + broadcast kernel over NVLink peer memory (csrc/tp_collective.cu)", "unit": "tokens/s", "n_gpus": world, "steps": steps, "scaling": "strong",
+            "collective": "GEMM-fused reduce-scatter + reduce/residual/RMSNorm/broadcast kernel over NVLink peer memory (csrc/tp_collective.cu)",
+            "kernel_breakdown_one_sample_ms": {"gemm_incl_scatter_push": tp_prof["gemm"][0], "attention": tp_prof["attention"][0],
+                                               "reduce_norm_broadcast_and_waits": tp_prof["row"][0], "sampling": tp_prof["sampling"][0]}, "unit": "tokens/s", "n_gpus": world, "steps": steps, "scaling": "strong",
             "ms_per_step": ms / steps, "config": {"workload": "BASELINE configs[3]: ONE prompt, tensor-parallel attention/MLP/LM head over the GPUs",
                                                   "parallelism": f"tensor-parallel x{world}"},
             "tp_parity": {"logits_max_err_bf16_ulp_of_scale": max_ulp, "logits_mean_err_bf16_ulp_of_scale": mean_ulp,

@@ -192,15 +192,17 @@ int tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16
     a.x_shard = reinterpret_cast<__nv_bfloat16*>(x_shard);
     a.w = reinterpret_cast<const __nv_bfloat16*>(w);
     a.row0 = row0; a.nrows = nrows; a.d = d; a.eps = eps; a.epoch = epoch; a.done_counter = done_counter;
-    // bytes this rank moves: reads n_src fp32 rows + x, writes x + n_ranks bf16 rows
-    LaunchScope ls(LK_ROW, (double)nrows * d * (4.0 * n_src + 4.0 + 2.0 * n_ranks), stream);
     const bool pdl = pdl_mode() != 0;
     cudaError_t e;
+    {
+    // bytes this rank moves: reads n_src fp32 rows + x, writes x + n_ranks bf16 rows
+    LaunchScope ls(LK_ROW, (double)nrows * d * (4.0 * n_src + 4.0 + 2.0 * n_ranks), stream);
     switch ((d + 2047) / 2048) {
         case 1: e = launch_ex(tp_reduce_norm_kernel<1>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
         case 2: e = launch_ex(tp_reduce_norm_kernel<2>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
         case 3: e = launch_ex(tp_reduce_norm_kernel<3>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
         default: e = launch_ex(tp_reduce_norm_kernel<4>, dim3(nrows), dim3(kTpThreads), 0, stream, pdl, false, a); break;
+    }
     }
     MMDP_CUDA(e);
     // the consumer of xn (the next column-parallel GEMM) needs every rank's rows: wait for phase 1 of all ranks
