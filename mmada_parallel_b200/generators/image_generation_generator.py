@@ -88,18 +88,15 @@ def generate_image(
     sampled_ws = torch.empty(cap, dtype=torch.int32, device=device)
     selp_ws = torch.empty(cap, dtype=torch.float32, device=device)
     unk_ws = torch.empty(cap, dtype=torch.uint8, device=device)
-    if debug:
-        print("=== generate_image debug start ===")
-        print(f"device={device}, seq_len={seq_len}, code_start={code_start}, codebook_size={codebook_size}")
-        print(f"text_vocab_size={text_vocab_size}, vocab_offset={off}")
-        print(f"Initial x.shape={tuple(x.shape)}, initial unknown_cnt={vq_len}")
-        print("==================================")
+    if debug:   # (the reference prints shapes and token samples per step; this mirror reports the per-step counts only)
+        print(f"[generate_image] {device}: {vq_len} masked VQ positions of {seq_len}, {timesteps} steps, vocab offset {off}, "
+              f"codebook {codebook_size}, cfg {cfg_scale}")
     for step in range(timesteps):
         flat_idx = (x[0] == mask_token_id).nonzero(as_tuple=False)[:, 0]                         # the step's read-back (:92)
         n = int(flat_idx.numel())
-        if n == 0:
+        if n == 0:                                                                               # :92-95 early exit
             if debug:
-                print(f"[step {step}] All tokens filled, breaking early.")
+                print(f"[generate_image] step {step}: nothing left to fill")
             break
         if step < timesteps - 1:                                                                 # :99-103, on the CPU like the oracle
             frac = noise_schedule(torch.tensor([(step + 1) / timesteps]))
@@ -107,8 +104,7 @@ def generate_image(
         else:
             keep_n = 0
         if debug:
-            print(f"\n--- step {step} ---")
-            print(f"unknown_cnt={n}, keep_n={keep_n}")
+            print(f"[generate_image] step {step}: {n} masked, {keep_n} stay masked")
         rows = flat_idx.to(torch.int32)
         model.forward_rows(x, rows_b=rows, col0_b=off, ncols_b=codebook_size, out_b=cond_vq[:n])  # :127 / :158
         if use_cfg:
@@ -139,6 +135,5 @@ def generate_image(
     vq_ids = x[0, code_start:-2]                                                                 # :236-238
     vq_ids = vq_ids[vq_ids != newline_id].view(1, seq_len)
     if debug:
-        print("=== generate_image debug end ===")
-        print(f"final vq_ids.shape={tuple(vq_ids.shape)}")
+        print(f"[generate_image] done: ids {tuple(vq_ids.shape)}")
     return vq_ids
