@@ -438,7 +438,7 @@ def measure_variant_m(args, rank: int, world: int, device: str, steps: int, warm
            "ms_per_step": ms / steps, "scaling": "weak",
            "config": {"workload": "MMaDA-Parallel-M 8B (BASELINE configs[4] shape per GPU): 1 prompt per GPU, L=2341, CFG batch 2 on each of 128 "
                                   "steps, 64 image steps, text_cfg=2.5, image_cfg=4.0", "parallelism": f"replicas x{world} (no collective)",
-                      "gemm_kernel": "1-CTA persistent kernel (M = 4682: 37 m-tiles); the cta_group::2 pair kernel is routed only by MMDP_GEMM_PAIR"},
+                      "gemm_kernel": "cta_group::2 pair kernel (M = 4682: 19 pair m-tiles; the default for M > 256, MMDP_GEMM_PAIR=0 routes the 1-CTA kernel)"},
            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": int(inp.numel() * 16), "d2h_bytes_per_step": 256 * 8},
            "algorithmic_pflop_per_sample": flops / 1e15,
            "whole_step_tflops_per_gpu": flops * steps / (ms / 1e3) / 1e12}

@@ -23,6 +23,9 @@ template <int BN> struct PairCfg {
     static constexpr int kStageBytes = kPABytes + kBHalfBytes;  // per CTA
     static constexpr int kStages = (BN == 256) ? 6 : 7;
     static constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + 4 * kScatStageFloats * 4;  // + reduce-scatter staging
+    // epilogues whose 256-wide tile can be cut into two independent 128-wide halves (the rotary epilogue works per 128-column
+    // head; the SwiGLU tile is [128 gate | 128 up] and cannot)
+    template <int EPI> static constexpr bool can_split() { return BN == 256 && (EPI == EPI_PLAIN || EPI == EPI_RESID || EPI == EPI_QKVROPE); }
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -78,7 +81,8 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 
 template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmBh, const GemmParams p) {
     constexpr int kStages = PairCfg<BN>::kStages;
     constexpr int kStageBytes = PairCfg<BN>::kStageBytes;
     static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || EPI == EPI_F32 || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
@@ -126,27 +130,38 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_k = (p.K + P_BK - 1) / P_BK;
     const int num_tiles = num_m * num_n;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    // Tail N-split (PairCfg::kCanSplit epilogues, p.nsplit_tail > 0): the tiles of the partial last wave are each cut into two
+    // 256 x BN/2 units, so that the wave takes about half a tile time instead of a whole one. Units [0, t_full) are whole
+    // tiles, unit t_full + 2 i + h is half h of tile t_full + i. A half unit runs the same K loop on its own columns:
+    // results are bit-identical to the unsplit kernel, no exchange between units.
+    constexpr bool kCanSplit = PairCfg<BN>::template can_split<EPI>();
+    const int t_full = kCanSplit ? num_tiles - p.nsplit_tail : num_tiles;
+    const int num_units = t_full + 2 * (num_tiles - t_full);
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
         if (elect_one_sync()) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+                const bool half = kCanSplit && unit >= t_full;
+                const int tile = half ? t_full + ((unit - t_full) >> 1) : unit;
                 const int m_blk = tile % num_m, n_blk = tile / num_m;
                 const int row0 = m_blk * 2 * P_BM + (int)rank * P_BM;       // this CTA's 128 rows of A
-                const int wrow0 = n_blk * BN + (int)rank * (BN / 2);         // this CTA's half of the W tile
+                // this CTA's half of the W rows of the unit (BN rows, or BN/2 for a half unit)
+                const int wrow0 = half ? n_blk * BN + ((unit - t_full) & 1) * (BN / 2) + (int)rank * (BN / 4) : n_blk * BN + (int)rank * (BN / 2);
+                const uint32_t tx = half ? 2 * (kPABytes + PairCfg<BN>::kBHalfBytes / 2) : 2 * kStageBytes;  // bytes of both CTAs
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[s]), 0);
                     if (leader) {
-                        mbar_expect_tx(&full_bar[s], 2 * kStageBytes);  // bytes of both CTAs
+                        mbar_expect_tx(&full_bar[s], tx);
                     } else {
                         mbar_arrive_cluster(leader_full);
                     }
                     uint8_t* sa = smem + s * kStageBytes;
                     tma_load_2d_pair(sa, &tmA, leader_full, kb * P_BK, row0);
-                    tma_load_2d_pair(sa + kPABytes, &tmB, leader_full, kb * P_BK, wrow0);
+                    tma_load_2d_pair(sa + kPABytes, half ? &tmBh : &tmB, leader_full, kb * P_BK, wrow0);
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
@@ -155,12 +170,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && elect_one_sync()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * P_BM, BN);
+            constexpr uint32_t idesc_whole = umma_idesc_bf16(2 * P_BM, BN);
+            constexpr uint32_t idesc_half = umma_idesc_bf16(2 * P_BM, kCanSplit ? BN / 2 : BN);
             int s = 0;
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+                const uint32_t idesc = (kCanSplit && unit >= t_full) ? idesc_half : idesc_whole;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -186,14 +203,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ew = warp - 4;
         int as = 0;
         uint32_t aph = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+            const bool half = kCanSplit && unit >= t_full;
+            const int tile = half ? t_full + ((unit - t_full) >> 1) : unit;
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             mbar_wait(&tmem_full[as], aph);
             tcgen05_fence_after();
             const int row = m_blk * 2 * P_BM + (int)rank * P_BM + ew * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-            gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
+            if constexpr (kCanSplit) {
+                if (half)
+                    gemm_epilogue_tile<EPI, BN / 2>(p, tbase, row, row_ok, 2 * n_blk + ((unit - t_full) & 1), scat_stage + ew * kScatStageFloats);
+                else
+                    gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
+            } else {
+                gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
@@ -213,7 +239,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int EPI, int BN>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, GemmParams& p, cudaStream_t stream) {
     static unsigned long long attr_set = 0;  // bit per device
     int dev = 0;
     MMDP_CUDA(cudaGetDevice(&dev));
@@ -224,8 +250,13 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     const int num_tiles = ((p.M + 2 * P_BM - 1) / (2 * P_BM)) * ((p.N + BN - 1) / BN);
     const int pairs = num_sms() / 2;
     const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
+    // tail N-split: a partial last wave of at most half the clusters, and a tile width that divides N (whole half tiles)
+    const int tail = num_tiles % pairs;
+    p.nsplit_tail = (PairCfg<BN>::template can_split<EPI>() && opt(OPT_GEMM_NSPLIT_TAIL) && num_tiles > pairs && tail > 0 &&
+                     2 * tail <= pairs && p.N % BN == 0) ? tail : 0;
     LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
-    MMDP_CUDA(launch_ex(gemm_pair_kernel<EPI, BN>, dim3(grid), dim3(kPairThreads), PairCfg<BN>::kSmem, stream, pdl_mode() != 0, false, tmA, tmB, p));
+    MMDP_CUDA(launch_ex(gemm_pair_kernel<EPI, BN>, dim3(grid), dim3(kPairThreads), PairCfg<BN>::kSmem, stream, pdl_mode() != 0, false, tmA, tmB,
+                        p.nsplit_tail ? tmBh : tmB, p));
     return 0;
 }
 
@@ -252,20 +283,22 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
     CUtensorMap tmA, tmB;
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, P_BM, P_BK)) return -1;
     if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn / 2, P_BK)) return -1;
+    CUtensorMap tmBh = tmB;  // box of bn / 4 W rows: one CTA's share of a half unit (tail N-split)
+    if (bn == 256 && epi != EPI_SWIGLU && epi != EPI_F32 && make_tmap_2d_bf16(&tmBh, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn / 4, P_BK)) return -1;
     switch (epi) {
         case EPI_PLAIN:
-            return bn == 192 ? launch_pair<EPI_PLAIN, 192>(tmA, tmB, p, stream) : launch_pair<EPI_PLAIN, 256>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_pair<EPI_PLAIN, 192>(tmA, tmB, tmBh, p, stream) : launch_pair<EPI_PLAIN, 256>(tmA, tmB, tmBh, p, stream);
         case EPI_RESID:
-            return bn == 192 ? launch_pair<EPI_RESID, 192>(tmA, tmB, p, stream) : launch_pair<EPI_RESID, 256>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_pair<EPI_RESID, 192>(tmA, tmB, tmBh, p, stream) : launch_pair<EPI_RESID, 256>(tmA, tmB, tmBh, p, stream);
         case EPI_F32:
-            return bn == 192 ? launch_pair<EPI_F32, 192>(tmA, tmB, p, stream) : launch_pair<EPI_F32, 256>(tmA, tmB, p, stream);
+            return bn == 192 ? launch_pair<EPI_F32, 192>(tmA, tmB, tmBh, p, stream) : launch_pair<EPI_F32, 256>(tmA, tmB, tmBh, p, stream);
         case EPI_SWIGLU:
-            return launch_pair<EPI_SWIGLU, 256>(tmA, tmB, p, stream);
+            return launch_pair<EPI_SWIGLU, 256>(tmA, tmB, tmBh, p, stream);
         case EPI_QKVROPE:
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
             p.pos_map = qa->pos_map; p.Tq = qa->Tq;
-            return launch_pair<EPI_QKVROPE, 256>(tmA, tmB, p, stream);
+            return launch_pair<EPI_QKVROPE, 256>(tmA, tmB, tmBh, p, stream);
         default:
             return set_error("gemm_pair: unknown epilogue");
     }

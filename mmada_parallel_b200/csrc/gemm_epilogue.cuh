@@ -42,6 +42,8 @@ struct GemmParams {
     // tile order: group_m == 0 -> M-fastest over all m-tiles; > 0 -> M-fastest inside groups of group_m m-tiles, all n-tiles
     // of a group before the next group (keeps the group's A rows L2-resident while the weights stream)
     int group_m;
+    // CTA-pair kernel: number of tiles of the partial last wave that are cut into two half-width units (gemm2.cu)
+    int nsplit_tail;
 };
 
 __host__ __device__ __forceinline__ void gemm_tile_coords(int tl, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
@@ -193,7 +195,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                     const size_t drow = (region == 0 || !p.pos_map) ? (size_t)row : (size_t)b * p.L + pos;  // k rows go to their sequence position
                     __nv_bfloat16* dst = (region == 0 ? p.q : p.k) + drow * p.d_model + (n0 - region * p.d_model);
 #pragma unroll 1
-                    for (int hc = 0; hc < 4; ++hc) {  // (head in tile) x (32-col chunk of the first half)
+                    for (int hc = 0; hc < BN / 64; ++hc) {  // (head in tile) x (32-col chunk of the first half)
                         const int head = hc >> 1, cc = hc & 1;
                         uint32_t x1[32], x2[32];
                         tmem_ld_32x32b_x32(tbase + head * 128 + cc * 32, x1);

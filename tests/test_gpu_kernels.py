@@ -331,3 +331,34 @@ def test_gemm_pair_kernel_bit_identical_to_single(M, N, K):
     finally:
         _lib.lib.mmdp_set_gemm_splitk(2)
         _lib.lib.mmdp_set_gemm_pair(1)
+
+
+@pytest.mark.parametrize("epi,M,N,K", [("qkv", 2414, 12288, 4096), ("plain", 2414, 23040, 448), ("resid", 2300, 4864, 576)])
+def test_gemm_pair_tail_nsplit_bit_identical(epi, M, N, K):
+    """Tail N-split of the CTA-pair kernel (gemm2.cu): the tiles of a partial last wave are cut into two half-width units. Every
+    output element still sees the same K loop, so the result must equal the unsplit kernel's bit for bit (QKV + rotary at the
+    bench shape: 480 tiles = 6 waves of 74 + 36 tiles -> 72 half units; plain 900 tiles -> tail 12; residual 171 -> tail 23)."""
+    from mmada_parallel_b200 import _lib
+    from mmada_parallel_b200.model import rope_tables
+    torch.manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    w = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    if epi == "qkv":
+        H = N // 3 // 128
+        cos, sin = (t.cuda() for t in rope_tables(128, 500000.0, M))
+        fn = lambda: torch.cat([t.reshape(-1).float() for t in _lib.qkv_rope(a, w, H, M, cos, sin)])
+    elif epi == "plain":
+        fn = lambda: _lib.gemm_bf16(a, w, _lib.EPI_PLAIN).float()
+    else:
+        r = bf(torch.randn(M, N, device="cuda"))
+        fn = lambda: _lib.gemm_bf16(a, w, _lib.EPI_RESID, resid=r).float()
+    try:
+        _lib.check(_lib.lib.mmdp_set_option(b"gemm_nsplit_tail", 0))
+        ref = fn()
+        _lib.check(_lib.lib.mmdp_set_option(b"gemm_nsplit_tail", 1))
+        got = fn()
+        again = fn()
+    finally:
+        _lib.check(_lib.lib.mmdp_set_option(b"gemm_nsplit_tail", 1))
+    assert torch.equal(got, ref), epi
+    assert torch.equal(got, again)
