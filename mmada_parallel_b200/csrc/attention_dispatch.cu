@@ -9,8 +9,12 @@ namespace mmdp {
 int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
                      int Lpad, float scale, cudaStream_t stream, int Lq);
 
+int attention_fwd_v7(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
+                     int Lpad, float scale, cudaStream_t stream, int Lq);
+
 int attention_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int H, int L,
                   int Lpad, float scale, cudaStream_t stream, int Lq) {
+    if (opt(OPT_ATTN_VERSION) == 7) return attention_fwd_v7(q, k, vt, out, B, H, L, Lpad, scale, stream, Lq);
     return attention_fwd_v6(q, k, vt, out, B, H, L, Lpad, scale, stream, Lq);
 }
 

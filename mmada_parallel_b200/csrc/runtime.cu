@@ -53,6 +53,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"attn_poly", "MMDP_ATTN_POLY", 4, 0, false},
     {"rmsnorm_warp", "MMDP_RMSNORM_WARP", 1, 0, false},
     {"gemm_nsplit_tail", "MMDP_GEMM_NSPLIT_TAIL", 1, 0, false},
+    {"attn_version", "MMDP_ATTN_VERSION", 6, 0, false},
 };
 int opt(int id) {
     Opt& o = g_opts[id];
