@@ -10,8 +10,12 @@
 //     ncu shows 27 % issue efficiency and 32 % of their time waiting for S);
 //   * P goes back into the TMEM columns S was read from (bf16 pairs, 64 columns) and is the A operand of the PV MMA;
 //     lazy rescale, packed-fp32 exponent arithmetic and the exp2 share on the FMA pipe are v6's (attention_math.cuh);
-//   * 10 warps: 4 softmax warps per slot (thread = query row, 128 scores in registers), one TMA producer (K 3 stages, V^T 2
-//     stages, loads issued in the order the MMAs consume them), one MMA issuer. 224.25 KB shared memory;
+//   * 18 warps: EIGHT softmax warps per slot - two threads per query row, 64 of the block's 128 scores each (warps w and w + 4
+//     of a slot share a TMEM lane quarter); the row max is exchanged through shared memory behind a 64-thread named barrier,
+//     the row sums stay per thread until the end. ncu on the one-thread-per-row form: a softmax warp issues 0.28
+//     instructions per clock (fixed-latency dependency stalls) and its 2 180 cycles per block were 56 % of the slot's period,
+//     so the cure is more warps per scheduler, not fewer instructions. One TMA producer (K 3 stages, V^T 2 stages, loads
+//     issued in the order the MMAs consume them), one MMA issuer. 226.25 KB shared memory;
 //   * work units: pairs of query tiles (2p, 2p+1) of a head; the odd last tile of a head runs alone in slot 0. Units may be
 //     cut along the keys into pieces whose un-normalised partials (O, m, l) are merged by attention_combine7_kernel: the
 //     odd tiles always (they are the tail of the launch and a one-slot unit keeps the tensor core idle during its
@@ -26,12 +30,13 @@
 
 namespace mmdp {
 
-static constexpr int k7Threads = 320;  // warps 0-3 softmax slot 0, 4-7 softmax slot 1, 8 TMA producer, 9 MMA issuer
+static constexpr int k7Threads = 576;  // warps 0-7 softmax slot 0 (column half = (warp >> 2) & 1), 8-15 slot 1, 16 TMA producer, 17 MMA issuer
+static constexpr int k7WarpTma = 16, k7WarpMma = 17;
 static constexpr int k7BKV = 128;
 static constexpr int k7KStages = 3;
 static constexpr int k7VStages = 2;
 static constexpr int k7Tile = 128 * 128 * 2;  // 32 KB: a Q, K or V^T tile = two SWIZZLE_128B boxes of 128 rows x 64 columns
-static constexpr int k7Smem = (2 + k7KStages + k7VStages) * k7Tile + 256;
+static constexpr int k7Smem = (2 + k7KStages + k7VStages) * k7Tile + 256 + 2 * 2 * 128 * 4;  // + barriers + row-max exchange
 static constexpr int k7PartFloats = 128 * 128 + 256;  // one partial: O [128][128], m [128], l [128]
 
 struct Attn7Params {
@@ -44,7 +49,7 @@ struct Attn7Params {
 };
 
 template <int POLY>
-__global__ void __launch_bounds__(k7Threads, 1)
+__global__ void __maxnreg__(112)
 attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const Attn7Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -66,6 +71,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* p_full = bars + 13;   // [2] per slot: the four softmax warps have published P(j)
     uint64_t* o_full = bars + 15;   // [2] per slot: last PV retired
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+    float* xchg = reinterpret_cast<float*>(bars + 32);  // [slot][column half][row]: row max / row sum exchange between the two threads of a row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -102,7 +108,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int n_kv = je - jb;  // >= 1 (the host never creates an empty piece)
     const bool partial = c > 1;
 
-    if (warp == 9 && lane == 0) {
+    if (warp == k7WarpMma && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < k7KStages; ++s) {
             mbar_init(&k_full[s], 1);
@@ -112,12 +118,12 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
-            mbar_init(&p_full[s], 4);
+            mbar_init(&p_full[s], 8);
             mbar_init(&o_full[s], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 8) {
+    if (warp == k7WarpTma) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmK);
@@ -134,7 +140,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     pdl_wait();
     // TMEM columns: S(slot) at slot * 128 (P(slot) = packed bf16 pairs in its first 64 columns), O(slot) at 256 + slot * 128
 
-    if (warp == 8) {
+    if (warp == k7WarpTma) {
         // ===================== TMA producer: Q tiles, then K(0), V(0), K(1), V(1), ... =====================
         if (elect_one_sync()) {
             mbar_expect_tx(q_full, ntile * k7Tile);
@@ -159,7 +165,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == k7WarpMma) {
         // ===================== MMA issuer =====================
         if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
@@ -212,34 +218,43 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
         __syncwarp();
-    } else if ((warp >> 2) < ntile) {
-        // ===================== softmax (slot = warp / 4, thread = query row) =====================
-        const int t = warp >> 2;
-        const int r = (warp & 3) * 32 + lane;
-        const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem_base + t * 128 + lane_off, tO = tmem_base + 256 + t * 128 + lane_off;
-        float m_used = -INFINITY, l_run = 0.f;
+    } else if ((warp >> 3) < ntile) {
+        // ===================== softmax (slot = warp / 8; two threads per query row: column half hf = (warp / 4) % 2) =====================
+        const int t = warp >> 3, hf = (warp >> 2) & 1, qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_off, tO = tmem_base + 256 + t * 128 + hf * 64 + lane_off;
+        float* x_mine = xchg + (t * 2 + hf) * 128 + r;
+        const float* x_other = xchg + (t * 2 + (hf ^ 1)) * 128 + r;
+        const int bar_id = 1 + t * 4 + qd;  // named barrier of the two warps that share these 32 rows
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+        float m_used = -INFINITY, l_run = 0.f;  // l_run: sum over THIS thread's columns only
         constexpr float kLazy = 8.0f;  // raise the running max only when it is exceeded by more than 2^8
 
         for (int j = 0; j < n_kv; ++j) {
-            const int nvalid = p.L - (jb + j) * k7BKV;
+            const int nvalid = p.L - (jb + j) * k7BKV - hf * 64;  // valid columns among this thread's 64
             mbar_wait(&s_full[t], j & 1);
             tcgen05_fence_after();
-            uint32_t sv[128];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(tS + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[q * 32]));
+            uint32_t sv[64];
+            tmem_ld_32x32b_x32(tS + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32b_x32(tS + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
             tmem_ld_wait();
-            if (nvalid < k7BKV) {
+            if (nvalid < 64) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
+                for (int i = 0; i < 64; ++i)
                     if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
             }
             float m8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) m8[i] = __uint_as_float(sv[i]);
 #pragma unroll
-            for (int i = 8; i < 128; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(sv[i]));
-            const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+            for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(sv[i]));
+            float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+            // row max over both column halves (the partner thread computes the same value: max is exact and commutative)
+            *x_mine = mx;
+            pair_sync();
+            mx = fmaxf(mx, *x_other);
+            pair_sync();  // the partner has read before this thread overwrites its slot in the next block
 
             // lazy rescale decision (v6's): only when this row's max exceeds the max in use by more than 2^kLazy (always on block 0)
             const bool need = (mx - m_used) * p.scale_log2 > kLazy;  // m_used = -inf on block 0 -> true
@@ -250,10 +265,10 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float mneg = -m_used * p.scale_log2;
 
             if (any_need && j >= 1) {
-                // rare: rescale O (TMEM). S(j) is complete, hence PV(j-1) - issued before QK(j) by the same thread - has
-                // retired; PV(j) cannot start before this warp publishes P(j) below.
+                // rare: rescale this thread's 64 columns of O (TMEM). S(j) is complete, hence PV(j-1) - issued before QK(j) by
+                // the same thread - has retired; PV(j) cannot start before all eight warps publish P(j) below.
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int cc = 0; cc < 2; ++cc) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(tO + cc * 32, v);
                     tmem_ld_wait();
@@ -262,51 +277,50 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tmem_st_32x32b_x32(tO + cc * 32, v);
                 }
             }
-            // P = 2^((s - m_used) * c) as bf16 pairs into the first 64 columns of S (all 128 scores of this row are in registers)
+            // P = 2^((s - m_used) * c) as bf16 pairs: this thread's 64 scores -> 32 packed columns at hf * 32 of the S region.
+            // (the partner may still be reading ITS columns hf' * 64 ... of S: columns [32, 64) written by hf = 1 belong to
+            // hf = 0's scores - hence the pair_sync above, after both threads hold their scores in registers)
             uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
-            {
-                uint32_t pk[32];
-                softmax_exp_block<64, POLY>(sv, p.scale_log2, mneg, pk, acc);
-                tmem_st_32x32b_x32(tS, pk);
-            }
-            {
-                uint32_t pk[32];
-                softmax_exp_block<64, POLY>(sv + 64, p.scale_log2, mneg, pk, acc);
-                tmem_st_32x32b_x32(tS + 32, pk);
-            }
+            uint32_t pk[32];
+            softmax_exp_block<64, POLY>(sv, p.scale_log2, mneg, pk, acc);
+            tmem_st_32x32b_x32(tS + hf * 32, pk);
             l_run = fmaf(l_run, alpha, f32x2_sum4(acc));
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
         }
-        // epilogue: O / l (or the un-normalised partial of this key piece)
+        // row sum over both halves
+        *x_mine = l_run;
+        pair_sync();
+        const float l_row = (hf == 0) ? l_run + *x_other : *x_other + l_run;  // same operand order in both threads
+        // epilogue: O / l (or the un-normalised partial of this key piece); this thread handles columns [hf * 64, hf * 64 + 64)
         mbar_wait(&o_full[t], 0);
         tcgen05_fence_after();
         const int qt = qt0 + t;
         const int qrow = qt * 128 + r;
         if (partial) {
             float* slot = p.part_ws + (size_t)(part0 + t * c + piece) * k7PartFloats;
-            if (qrow < p.Lq) {
+            if (qrow < p.Lq && hf == 0) {
                 slot[128 * 128 + r] = m_used;
-                slot[128 * 128 + 128 + r] = l_run;
+                slot[128 * 128 + 128 + r] = l_row;
             }
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 2; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tO + cc * 32, v);
                 tmem_ld_wait();
                 if (qrow < p.Lq) {
-                    uint4* d4 = reinterpret_cast<uint4*>(slot + (size_t)r * 128 + cc * 32);
+                    uint4* d4 = reinterpret_cast<uint4*>(slot + (size_t)r * 128 + hf * 64 + cc * 32);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
         } else {
-            const float inv_l = 1.0f / l_run;
-            __nv_bfloat16* orow = p.out + (size_t)(b * p.Lq + (qrow < p.Lq ? qrow : 0)) * p.d_model + h * 128;
+            const float inv_l = 1.0f / l_row;
+            __nv_bfloat16* orow = p.out + (size_t)(b * p.Lq + (qrow < p.Lq ? qrow : 0)) * p.d_model + h * 128 + hf * 64;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 2; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tO + cc * 32, v);
                 tmem_ld_wait();
@@ -324,7 +338,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == k7WarpTma) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
