@@ -49,7 +49,7 @@ struct Attn7Params {
 };
 
 template <int POLY>
-__global__ void __maxnreg__(112)
+__global__ void __maxnreg__(96)
 attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const Attn7Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -236,8 +236,8 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_wait(&s_full[t], j & 1);
             tcgen05_fence_after();
             uint32_t sv[64];
-            tmem_ld_32x32b_x32(tS + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-            tmem_ld_32x32b_x32(tS + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) tmem_ld_32x32b_x16(tS + hf * 64 + q4 * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[q4 * 16]));
             tmem_ld_wait();
             if (nvalid < 64) {
 #pragma unroll
@@ -268,22 +268,25 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 // rare: rescale this thread's 64 columns of O (TMEM). S(j) is complete, hence PV(j-1) - issued before QK(j) by
                 // the same thread - has retired; PV(j) cannot start before all eight warps publish P(j) below.
 #pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tO + cc * 32, v);
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tO + cc * 16, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                    tmem_st_32x32b_x32(tO + cc * 32, v);
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                    tmem_st_32x32b_x16(tO + cc * 16, v);
                 }
             }
             // P = 2^((s - m_used) * c) as bf16 pairs: this thread's 64 scores -> 32 packed columns at hf * 32 of the S region.
             // (the partner may still be reading ITS columns hf' * 64 ... of S: columns [32, 64) written by hf = 1 belong to
             // hf = 0's scores - hence the pair_sync above, after both threads hold their scores in registers)
             uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
-            uint32_t pk[32];
-            softmax_exp_block<64, POLY>(sv, p.scale_log2, mneg, pk, acc);
-            tmem_st_32x32b_x32(tS + hf * 32, pk);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {  // 16-column stores: short register vectors (the budget is 96 registers with 18 warps)
+                uint32_t pk[16];
+                softmax_exp_block<32, POLY>(sv + hh * 32, p.scale_log2, mneg, pk, acc);
+                tmem_st_32x32b_x16(tS + hf * 32 + hh * 16, pk);
+            }
             l_run = fmaf(l_run, alpha, f32x2_sum4(acc));
             tmem_st_wait();
             tcgen05_fence_before();
