@@ -46,6 +46,7 @@ struct Attn7Params {
     float scale_log2;
     int n_pair, c_pair;      // pair units (two tiles each) and the number of key pieces each is cut into (1 = direct output)
     int n_single, c_single;  // odd last tiles (one per (b, h) when n_qt is odd) and their pieces
+    int probe;               // timing probes (results are garbage for 1-3): 1 softmax threads skip their work, 2 no PV MMAs, 3 no QK MMAs, 4 every lane polls the barriers
 };
 
 template <int POLY>
@@ -175,7 +176,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t off = (k >> 2) * (k7Tile / 2);
-                    umma_bf16_ss(tmem_base + t * 128, umma_desc_kmajor_sw128(aQ + off) + (k & 3) * 2,
+                    if (p.probe != 3) umma_bf16_ss(tmem_base + t * 128, umma_desc_kmajor_sw128(aQ + off) + (k & 3) * 2,
                                  umma_desc_kmajor_sw128(aK + off) + (k & 3) * 2, idesc, k != 0);
                 }
             };
@@ -199,7 +200,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t aV = smem_u32(sV + vs * k7Tile);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
+                        if (p.probe != 2) umma_bf16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
                                      umma_desc_kmajor_sw128(aV + (k >> 2) * (k7Tile / 2)) + (k & 3) * 2, idesc, (j | k) != 0);
                     if (t == ntile - 1) umma_commit(&v_empty[vs]);
                     if (more) {
@@ -233,8 +234,14 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         for (int j = 0; j < n_kv; ++j) {
             const int nvalid = p.L - (jb + j) * k7BKV - hf * 64;  // valid columns among this thread's 64
-            mbar_wait(&s_full[t], j & 1);
+            mbar_wait_warp(&s_full[t], j & 1, p.probe != 4);
             tcgen05_fence_after();
+            if (p.probe == 1) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+                continue;
+            }
             uint32_t sv[64];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) tmem_ld_32x32b_x16(tS + hf * 64 + q4 * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[q4 * 16]));
@@ -298,7 +305,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         pair_sync();
         const float l_row = (hf == 0) ? l_run + *x_other : *x_other + l_run;  // same operand order in both threads
         // epilogue: O / l (or the un-normalised partial of this key piece); this thread handles columns [hf * 64, hf * 64 + 64)
-        mbar_wait(&o_full[t], 0);
+        mbar_wait_warp(&o_full[t], 0, p.probe != 4);
         tcgen05_fence_after();
         const int qt = qt0 + t;
         const int qrow = qt * 128 + r;
@@ -425,6 +432,7 @@ int attention_fwd_v7(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     p.n_pair = B * H * (p.n_qt >> 1);
     p.n_single = (p.n_qt & 1) ? B * H : 0;
     p.c_pair = p.c_single = 1;
+    p.probe = opt(OPT_ATTN_PROBE);
     const int n_kvb = (L + k7BKV - 1) / k7BKV, sms = num_sms();
     // pieces of `want` or fewer key blocks each, none empty: piece i covers blocks [i * per, (i + 1) * per), per = ceil(n_kvb / c)
     auto fit = [&](int want) {

@@ -71,6 +71,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Warp-collective wait (all 32 lanes converged): ONE lane polls, the others sleep at the warp barrier and then observe the
+// completed phase with a single try_wait of their own (each waiting thread needs its own acquire). A warp that spins with
+// all 32 lanes issues 32x the polls on the barrier's shared-memory word; with 8-16 idle warps per CTA that traffic delays
+// the arrivals everybody is waiting for (tcgen05.commit, TMA complete_tx) - measured on the attention kernels.
+// `collective` = false falls back to every lane polling (A/B switch).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool collective = true) {
+    if (collective) {
+        if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+        __syncwarp();
+    }
+    mbar_wait(bar, parity);
+}
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -54,6 +54,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"rmsnorm_warp", "MMDP_RMSNORM_WARP", 1, 0, false},
     {"gemm_nsplit_tail", "MMDP_GEMM_NSPLIT_TAIL", 1, 0, false},
     {"attn_version", "MMDP_ATTN_VERSION", 6, 0, false},
+    {"attn_probe", "MMDP_ATTN_PROBE", 0, 0, false},
 };
 int opt(int id) {
     Opt& o = g_opts[id];
