@@ -14,7 +14,7 @@ vt = torch.zeros(B, H, 128, Lpad, dtype=torch.bfloat16, device="cuda")
 vt[..., :L] = torch.randn(B, H, 128, L, device="cuda").to(torch.bfloat16)
 flops = 4.0 * B * H * L * L * 128
 for rnd in range(2):
-    for ver, probe in ((7, 0), (7, 4), (7, 1), (7, 2), (7, 3), (6, 0), (6, 4)):
+    for ver, probe in ((7, 0), (7, 5), (7, 4), (7, 1), (6, 0), (6, 5), (6, 4)):
         _lib.check(_lib.lib.mmdp_set_option(b"attn_version", ver))
         _lib.check(_lib.lib.mmdp_set_option(b"attn_probe", probe))
         for _ in range(3):
