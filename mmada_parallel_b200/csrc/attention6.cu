@@ -45,7 +45,7 @@ template <int POLY>
 __global__ void __launch_bounds__(k6Threads, 2)
 attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int H, int L, int d_model,
-                    float scale_log2, int n_full, int splits, float* __restrict__ part_ws, int Lq, int warp_poll) {
+                    float scale_log2, int n_full, int splits, float* __restrict__ part_ws, int Lq) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
@@ -185,7 +185,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t u = (jj >> 1) & 1;
                     const uint32_t aV = smem_u32(sV + s * k6VBytes);
                     mbar_wait(&v_full[s], u);
-                    if (warp_poll == 5) mbar_wait_spin(&p_full[s], u); else mbar_wait(&p_full[s], u);
+                    mbar_wait(&p_full[s], u);
                     tcgen05_fence_after();
 #pragma unroll
                     for (int k = 0; k < k6BKV / 16; ++k)
@@ -207,7 +207,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < n_kv; ++j) {
             const int s = j & 1;
             const int nvalid = L - (jb + j) * k6BKV;
-            if (warp_poll == 5) mbar_wait_spin(&s_full[s], (j >> 1) & 1); else mbar_wait_warp(&s_full[s], (j >> 1) & 1, warp_poll == 4);
+            mbar_wait(&s_full[s], (j >> 1) & 1);
             tcgen05_fence_after();
             uint32_t sv[64];
             tmem_ld_32x32b_x32(tS0 + s * k6BKV + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -265,7 +265,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // epilogue: O / l. Not pv_done: when the last softmax block is done only PV(n_kv-3) is known to have retired, and
         // a parity wait two phases ahead of the barrier returns at once (it did: rare wrong rows, found by the determinism
         // check of tests/test_gpu_model.py::test_full_size_properties).
-        mbar_wait_warp(o_full, 0, warp_poll == 4);
+        mbar_wait(o_full, 0);
         tcgen05_fence_after();
         const int qrow = qt * 128 + r;
         if (piece >= 0) {
@@ -410,7 +410,7 @@ int attention_fwd_v6(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
             attr_set |= 1ull << (dev & 63);
         }
         MMDP_CUDA(launch_ex(kernel, dim3(grid), dim3(k6Threads), k6Smem, stream, pdl, false, tmQ, tmK, tmVt, out, H, L, d_model,
-                            scale_log2, n_full, splits, part_ws, Lq, opt(OPT_ATTN_PROBE)));
+                            scale_log2, n_full, splits, part_ws, Lq));
         return 0;
     };
     if (poly == 2) { if (launch(attention_v6_kernel<2>)) return -1; }

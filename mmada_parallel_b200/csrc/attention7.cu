@@ -46,7 +46,7 @@ struct Attn7Params {
     float scale_log2;
     int n_pair, c_pair;      // pair units (two tiles each) and the number of key pieces each is cut into (1 = direct output)
     int n_single, c_single;  // odd last tiles (one per (b, h) when n_qt is odd) and their pieces
-    int probe;               // timing probes (results are garbage for 1-3): 1 softmax threads skip their work, 2 no PV MMAs, 3 no QK MMAs; 4 one polling lane per softmax warp; 5 busy polling (test_wait) on S-ready / P-ready
+    int probe;               // timing probes (results are garbage): 1 softmax threads skip their work, 2 no PV MMAs, 3 no QK MMAs
 };
 
 template <int POLY>
@@ -195,7 +195,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(&v_full[vs], (j >> 1) & 1);
                 for (int t = 0; t < ntile; ++t) {
                     // O(t) += P(t)(j) V(j): A = P from tensor memory (8 columns per K=16 step), B = V^T (two halves of 64 keys)
-                    if (p.probe == 5) mbar_wait_spin(&p_full[t], j & 1); else mbar_wait(&p_full[t], j & 1);
+                    mbar_wait(&p_full[t], j & 1);
                     tcgen05_fence_after();
                     const uint32_t aV = smem_u32(sV + vs * k7Tile);
 #pragma unroll
@@ -234,7 +234,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         for (int j = 0; j < n_kv; ++j) {
             const int nvalid = p.L - (jb + j) * k7BKV - hf * 64;  // valid columns among this thread's 64
-            if (p.probe == 5) mbar_wait_spin(&s_full[t], j & 1); else mbar_wait_warp(&s_full[t], j & 1, p.probe == 4);
+            mbar_wait(&s_full[t], j & 1);
             tcgen05_fence_after();
             if (p.probe == 1) {
                 tcgen05_fence_before();
@@ -305,7 +305,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         pair_sync();
         const float l_row = (hf == 0) ? l_run + *x_other : *x_other + l_run;  // same operand order in both threads
         // epilogue: O / l (or the un-normalised partial of this key piece); this thread handles columns [hf * 64, hf * 64 + 64)
-        mbar_wait_warp(&o_full[t], 0, p.probe == 4);
+        mbar_wait(&o_full[t], 0);
         tcgen05_fence_after();
         const int qt = qt0 + t;
         const int qrow = qt * 128 + r;

@@ -71,43 +71,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Busy-polling wait: mbarrier.test_wait never suspends the thread (try_wait may park it until the phase flips or a time limit
-// expires); used to measure the wake-up latency of the parked form on the critical hand-offs of the attention kernels.
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_test_wait(bar, parity)) {
-        if (++spins > (MMDP_WAIT_SPIN_LIMIT << 2)) {
-            printf("mmdp: mbarrier spin timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
-    }
-}
-
-// Warp-collective wait (all 32 lanes converged): ONE lane polls, the others sleep at the warp barrier and then observe the
-// completed phase with a single try_wait of their own (each waiting thread needs its own acquire). A warp that spins with
-// all 32 lanes issues 32x the polls on the barrier's shared-memory word; with 8-16 idle warps per CTA that traffic delays
-// the arrivals everybody is waiting for (tcgen05.commit, TMA complete_tx) - measured on the attention kernels.
-// `collective` = false falls back to every lane polling (A/B switch).
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool collective = false) {
-    if (collective) {
-        if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-        __syncwarp();
-    }
-    mbar_wait(bar, parity);
-}
-
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -112,6 +112,16 @@ def test_gemm_rejects_bad_arguments():
         _lib.gemm_bf16(a.cpu(), w.cpu())  # no CPU fallback
 
 
+@pytest.fixture(params=[6, 7])
+def attn_version(request):
+    """Both attention kernel generations (csrc/attention6.cu: the default; attention7.cu: one CTA per SM with two query tiles,
+    opt-in through MMDP_ATTN_VERSION / mmdp_set_option) run the same tests."""
+    from mmada_parallel_b200 import _lib
+    _lib.check(_lib.lib.mmdp_set_option(b"attn_version", request.param))
+    yield request.param
+    _lib.check(_lib.lib.mmdp_set_option(b"attn_version", 6))
+
+
 def assert_attention_close(o, o_ref, what, ulps=4.0):
     """RELATIVE bound on the attention output against the fp32 softmax(QK^T)V reference. The kernel rounds P to bf16 before
     the PV product (relative 2^-9 per probability, averaging out over the row) and the output to bf16 (2^-9): the error of
@@ -137,7 +147,7 @@ def ref_rope(t, cos, sin):
 
 
 @pytest.mark.parametrize("B,L,H", [(1, 128, 2), (2, 200, 2), (1, 640, 4), (3, 77, 2), (1, 2414, 4)])
-def test_qkv_rope_and_attention(B, L, H):
+def test_qkv_rope_and_attention(B, L, H, attn_version):
     from mmada_parallel_b200 import _lib
     from mmada_parallel_b200.model import rope_tables
     torch.manual_seed(B * 1000 + L + H)
@@ -167,13 +177,13 @@ def test_qkv_rope_and_attention(B, L, H):
     assert_attention_close(o, o_ref, f"attention B{B} L{L} H{H}")
 
 
-def test_attention_lazy_rescale():
+def test_attention_lazy_rescale(attn_version):
     """The attention kernel against the fp32 reference, on random scores and on
     scores whose magnitude grows along the KV axis, so that the running row max jumps by far more than the lazy-rescale
     threshold (2^8) in many KV blocks - the path that rescales the TMEM-resident O accumulator."""
     from mmada_parallel_b200 import _lib
     scale = 1.0 / math.sqrt(128.0)
-    version = 6
+    version = attn_version
     try:
         for B, L, H, grow in [(2, 333, 2, 0.0), (1, 1000, 2, 60.0), (1, 129, 1, 200.0)]:
             torch.manual_seed(version * 100 + L)
@@ -195,7 +205,7 @@ def test_attention_lazy_rescale():
         pass
 
 
-def test_attention_bitwise_repeatable():
+def test_attention_bitwise_repeatable(attn_version):
     """The same attention launch repeated many times at the full sequence length must be bitwise identical. (A parity wait
     that could return two mbarrier phases early made v6 read O before the last PV MMAs retired - rare, timing dependent,
     a few query rows per launch; this is the stress that exposes such races.) Two co-resident CTAs per SM, B=2."""
@@ -236,7 +246,7 @@ def test_rmsnorm_embed_lfq():
     assert torch.equal(_lib.lfq_decode(vq, 13).cpu(), lfq_codebook_entry(vq.cpu(), 13))
 
 
-def test_attention_full_length_relative_error():
+def test_attention_full_length_relative_error(attn_version):
     """BASELINE sequence length, 32 heads (608 CTAs: two full waves + the KV-split partial wave and its combine pass) against
     the fp32 reference with the relative bound of assert_attention_close; also checks the split and unsplit tails agree."""
     from mmada_parallel_b200 import _lib
