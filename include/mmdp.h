@@ -105,6 +105,16 @@ typedef struct mmdp_tp_layer {
     const uint16_t* attn_norm;  /* [d] */
     const uint16_t* ff_norm;    /* [d] */
 } mmdp_tp_layer;
+/* Shared (peer-mapped) state of one ROW CHUNK of the tensor-parallel forward. The sequence rows are cut into n_chunks (1 or 2)
+ * contiguous chunks; inside a chunk rank r owns rows [r*R, (r+1)*R), R = ceil(rows of the chunk / n_ranks). With two chunks
+ * the attn_out / MLP part of a layer runs as two independent chains on two streams, so that one chunk's NVLink traffic
+ * (partial rows pushed from the GEMM epilogue, broadcast of the normalised rows) overlaps the other chunk's GEMMs. */
+typedef struct mmdp_tp_chunk {
+    uint16_t* x_shard;                           /* this rank's rows of the residual stream [R, d] */
+    float* const* recv[2];                       /* HOST arrays [n_ranks] of the two receive buffers of every rank ([n_ranks][R][d] fp32 each) */
+    uint32_t* const* flags;                      /* HOST array [n_ranks] of the flag arrays ([2][8] uint32 each) */
+    uint32_t* done_counter;
+} mmdp_tp_chunk;
 typedef struct mmdp_tp_ctx {
     int32_t d_model, n_heads_local, ff_local, n_layers, n_ranks, rank;
     float rms_eps;
@@ -112,13 +122,13 @@ typedef struct mmdp_tp_ctx {
     const uint16_t* wte; const uint16_t* ln_f; int64_t vocab;
     const float* cos_tab; const float* sin_tab;  /* [max_seq_len, 64] */
     uint16_t *q, *k, *att, *h, *vt;              /* work buffers: [M, d_attn] x3, [M, ff_local], [B, H_local, 128, Lpad] (pad columns zero) */
-    uint16_t* x_shard;                           /* [rows_per_rank, d] */
-    float* const* recv[2];                       /* HOST arrays [n_ranks] of the two receive buffers of every rank */
-    uint16_t* const* xn;                         /* HOST array [n_ranks] of the activation buffers */
-    uint32_t* const* flags;                      /* HOST array [n_ranks] of the flag arrays */
-    uint32_t* done_counter;
+    uint16_t* const* xn;                         /* HOST array [n_ranks] of the activation buffers [M, d] */
+    int32_t n_chunks;                            /* 1 or 2 */
+    int32_t chunk_rows0;                         /* rows of chunk 0 (chunk 1 holds the rest); ignored when n_chunks == 1 */
+    mmdp_tp_chunk chunk[2];
 } mmdp_tp_ctx;
-/* epoch0: the last epoch used so far; the call uses epoch0 + 1 ... epoch0 + 2 * n_layers + 1 (returned through *epoch_out). */
+/* epoch0: the last epoch used so far; the call uses epoch0 + 1 ... epoch0 + 2 * n_layers + 1 on every chunk's flags (returned
+ * through *epoch_out). With two chunks the call uses an internal second stream, forked from and joined back into `stream`. */
 MMDP_API int mmdp_tp_forward(const mmdp_tp_ctx* c, const int64_t* ids, int B, int L, uint32_t epoch0, uint32_t* epoch_out, void* stream);
 
 /* ---- epilogues of mmdp_gemm_bf16 ----------------------------------------------------------------------------- */

@@ -46,13 +46,16 @@ class TpLayer(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wo", "w13", "w2", "attn_norm", "ff_norm")]
 
 
+class TpChunk(C.Structure):
+    _fields_ = [("x_shard", C.c_void_p), ("recv", C.POINTER(C.c_void_p) * 2), ("flags", C.POINTER(C.c_void_p)), ("done_counter", C.c_void_p)]
+
+
 class TpCtx(C.Structure):
     _fields_ = [("d_model", C.c_int32), ("n_heads_local", C.c_int32), ("ff_local", C.c_int32), ("n_layers", C.c_int32),
                 ("n_ranks", C.c_int32), ("rank", C.c_int32), ("rms_eps", C.c_float), ("layers", C.POINTER(TpLayer)),
                 ("wte", C.c_void_p), ("ln_f", C.c_void_p), ("vocab", C.c_int64), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
                 ("q", C.c_void_p), ("k", C.c_void_p), ("att", C.c_void_p), ("h", C.c_void_p), ("vt", C.c_void_p),
-                ("x_shard", C.c_void_p), ("recv", C.POINTER(C.c_void_p) * 2), ("xn", C.POINTER(C.c_void_p)),
-                ("flags", C.POINTER(C.c_void_p)), ("done_counter", C.c_void_p)]
+                ("xn", C.POINTER(C.c_void_p)), ("n_chunks", C.c_int32), ("chunk_rows0", C.c_int32), ("chunk", TpChunk * 2)]
 
 
 class ModelConfig(C.Structure):

@@ -210,38 +210,107 @@ MMDP_API int mmdp_gemm_f32_scatter(const uint16_t* A, int lda, const uint16_t* W
     return gemm_bf16(EPI_F32, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, nullptr, N, nullptr, 0, nullptr, (cudaStream_t)stream, &sc);
 }
 
+// second stream + events of the two-chunk tensor-parallel forward, one set per device
+struct TpSide { cudaStream_t s1 = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static int tp_side(TpSide** out) {
+    static TpSide sides[64];
+    int dev = 0;
+    MMDP_CUDA(cudaGetDevice(&dev));
+    TpSide& t = sides[dev & 63];
+    if (!t.s1) {
+        MMDP_CUDA(cudaStreamCreateWithFlags(&t.s1, cudaStreamNonBlocking));
+        MMDP_CUDA(cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming));
+        MMDP_CUDA(cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming));
+    }
+    *out = &t;
+    return 0;
+}
+
 MMDP_API int mmdp_tp_forward(const mmdp_tp_ctx* c, const int64_t* ids, int B, int L, uint32_t epoch0, uint32_t* epoch_out, void* stream) {
     if (!c || !ids || !epoch_out) return set_error("mmdp_tp_forward: null argument");
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t s0 = (cudaStream_t)stream;
     const int d = c->d_model, Hl = c->n_heads_local, da = Hl * 128, ffl = c->ff_local, tp = c->n_ranks;
     const int M = B * L, Lpad = ((L + 7) / 8) * 8;
-    const int R = (M + tp - 1) / tp, row0 = c->rank * R, nrows = (M - row0 < R ? M - row0 : R);
-    if (nrows < 1 || M - (tp - 1) * R < 1) return set_error("mmdp_tp_forward: %d tokens cannot be split over %d ranks with at least one row each", M, tp);
+    const int nch = c->n_chunks == 2 ? 2 : 1;
+    if (nch == 2 && (c->chunk_rows0 <= 0 || c->chunk_rows0 >= M)) return set_error("mmdp_tp_forward: chunk_rows0 must lie inside (0, %d)", M);
+    // row chunks: chunk ci covers sequence rows [m0, m0 + Mc); inside it rank r owns [r * R, (r + 1) * R)
+    struct Chunk { int m0, Mc, R, row0, nrows; cudaStream_t s; GemmScatter sc[2]; };
+    Chunk ch[2];
+    TpSide* side = nullptr;
+    if (nch == 2 && tp_side(&side)) return -1;
+    for (int ci = 0; ci < nch; ++ci) {
+        Chunk& k = ch[ci];
+        k.m0 = ci == 0 ? 0 : c->chunk_rows0;
+        k.Mc = nch == 1 ? M : (ci == 0 ? c->chunk_rows0 : M - c->chunk_rows0);
+        k.R = (k.Mc + tp - 1) / tp;
+        k.row0 = c->rank * k.R;
+        k.nrows = k.Mc - k.row0 < k.R ? k.Mc - k.row0 : k.R;
+        if (k.nrows < 1 || k.Mc - (tp - 1) * k.R < 1)
+            return set_error("mmdp_tp_forward: %d rows cannot be split over %d ranks with at least one row each", k.Mc, tp);
+        k.s = ci == 0 ? s0 : side->s1;
+        for (int b = 0; b < 2; ++b) {
+            k.sc[b] = GemmScatter{};
+            for (int r = 0; r < tp; ++r) k.sc[b].dst[r] = c->chunk[ci].recv[b][r];
+            k.sc[b].rows_per_rank = k.R; k.sc[b].slot = c->rank;
+        }
+    }
     const float scale = 1.0f / sqrtf(128.0f);
     uint32_t epoch = epoch0;
-    GemmScatter sc[2]{};
-    for (int b = 0; b < 2; ++b) {
-        for (int r = 0; r < tp; ++r) sc[b].dst[r] = c->recv[b][r];
-        sc[b].rows_per_rank = R; sc[b].slot = c->rank;
-    }
-    auto reduce = [&](int buf, const uint16_t* w) -> int {
-        return tp_reduce_norm(buf >= 0 ? c->recv[buf][c->rank] : nullptr, R, buf >= 0 ? tp : 0, c->xn, c->flags, tp, c->rank, c->x_shard, w, row0, nrows, d,
-                              c->rms_eps, ++epoch, c->done_counter, s);
+    // this rank's view of every rank's activation buffer, offset to the chunk's first row
+    uint16_t* xn_chunk[2][8];
+    for (int ci = 0; ci < nch; ++ci)
+        for (int r = 0; r < tp; ++r) xn_chunk[ci][r] = c->xn[r] + (size_t)ch[ci].m0 * d;
+    auto reduce = [&](int ci, int buf, const uint16_t* w, uint32_t ep) -> int {
+        const Chunk& k = ch[ci];
+        const mmdp_tp_chunk& cc = c->chunk[ci];
+        return tp_reduce_norm(buf >= 0 ? cc.recv[buf][c->rank] : nullptr, k.R, buf >= 0 ? tp : 0, xn_chunk[ci], cc.flags, tp, c->rank, cc.x_shard, w,
+                              k.row0, k.nrows, d, c->rms_eps, ep, cc.done_counter, k.s);
+    };
+    auto fork = [&]() -> int {  // the side stream continues after everything issued to the caller's stream so far
+        if (nch == 1) return 0;
+        MMDP_CUDA(cudaEventRecord(side->fork, s0));
+        MMDP_CUDA(cudaStreamWaitEvent(side->s1, side->fork, 0));
+        return 0;
+    };
+    auto join = [&]() -> int {
+        if (nch == 1) return 0;
+        MMDP_CUDA(cudaEventRecord(side->join, side->s1));
+        MMDP_CUDA(cudaStreamWaitEvent(s0, side->join, 0));
+        return 0;
     };
     const bf16* xn = (const bf16*)c->xn[c->rank];
-    if (embed_rows(ids + row0, (const bf16*)c->wte, (bf16*)c->x_shard, nrows, d, c->vocab, s, nullptr)) return -1;
-    if (reduce(-1, c->layers[0].attn_norm)) return -1;
-    QkvRopeArgs qa{(bf16*)c->q, (bf16*)c->k, (bf16*)c->vt, c->cos_tab, c->sin_tab, L, Lpad, da, Hl};
+    if (fork()) return -1;
+    ++epoch;
+    for (int ci = 0; ci < nch; ++ci) {
+        const Chunk& k = ch[ci];
+        if (embed_rows(ids + k.m0 + k.row0, (const bf16*)c->wte, (bf16*)c->chunk[ci].x_shard, k.nrows, d, c->vocab, k.s, nullptr)) return -1;
+        if (reduce(ci, -1, c->layers[0].attn_norm, epoch)) return -1;
+    }
     for (int li = 0; li < c->n_layers; ++li) {
         const mmdp_tp_layer& l = c->layers[li];
-        if (gemm_bf16(EPI_QKVROPE, xn, d, (const bf16*)l.wqkv, d, M, 3 * da, d, nullptr, 0, nullptr, 0, &qa, s)) return -1;
-        if (attention_fwd((const bf16*)c->q, (const bf16*)c->k, (const bf16*)c->vt, (bf16*)c->att, B, Hl, L, Lpad, scale, s)) return -1;
-        if (gemm_bf16(EPI_F32, (const bf16*)c->att, da, (const bf16*)l.wo, da, M, d, da, nullptr, d, nullptr, 0, nullptr, s, &sc[0])) return -1;
-        if (reduce(0, l.ff_norm)) return -1;
-        if (gemm_bf16(EPI_SWIGLU, xn, d, (const bf16*)l.w13, d, M, 2 * ffl, d, (bf16*)c->h, ffl, nullptr, 0, nullptr, s)) return -1;
-        if (gemm_bf16(EPI_F32, (const bf16*)c->h, ffl, (const bf16*)l.w2, ffl, M, d, ffl, nullptr, d, nullptr, 0, nullptr, s, &sc[1])) return -1;
-        if (reduce(1, li + 1 < c->n_layers ? c->layers[li + 1].attn_norm : c->ln_f)) return -1;
+        for (int ci = 0; ci < nch; ++ci) {
+            const Chunk& k = ch[ci];
+            QkvRopeArgs qa{(bf16*)c->q + (size_t)k.m0 * da, (bf16*)c->k + (size_t)k.m0 * da, (bf16*)c->vt, c->cos_tab, c->sin_tab, L, Lpad, da, Hl};
+            qa.chunked = nch > 1; qa.row0 = k.m0;
+            if (gemm_bf16(EPI_QKVROPE, xn + (size_t)k.m0 * d, d, (const bf16*)l.wqkv, d, k.Mc, 3 * da, d, nullptr, 0, nullptr, 0, &qa, k.s)) return -1;
+        }
+        // attention mixes all rows: both chunks' q / k / v^T must be complete, and it must be complete before either chain goes on
+        if (join()) return -1;
+        if (attention_fwd((const bf16*)c->q, (const bf16*)c->k, (const bf16*)c->vt, (bf16*)c->att, B, Hl, L, Lpad, scale, s0)) return -1;
+        if (fork()) return -1;
+        const uint32_t e1 = ++epoch, e2 = ++epoch;
+        for (int ci = 0; ci < nch; ++ci) {
+            const Chunk& k = ch[ci];
+            const bf16* att = (const bf16*)c->att + (size_t)k.m0 * da;
+            bf16* h = (bf16*)c->h + (size_t)k.m0 * ffl;
+            if (gemm_bf16(EPI_F32, att, da, (const bf16*)l.wo, da, k.Mc, d, da, nullptr, d, nullptr, 0, nullptr, k.s, &k.sc[0])) return -1;
+            if (reduce(ci, 0, l.ff_norm, e1)) return -1;
+            if (gemm_bf16(EPI_SWIGLU, xn + (size_t)k.m0 * d, d, (const bf16*)l.w13, d, k.Mc, 2 * ffl, d, h, ffl, nullptr, 0, nullptr, k.s)) return -1;
+            if (gemm_bf16(EPI_F32, h, ffl, (const bf16*)l.w2, ffl, k.Mc, d, ffl, nullptr, d, nullptr, 0, nullptr, k.s, &k.sc[1])) return -1;
+            if (reduce(ci, 1, li + 1 < c->n_layers ? c->layers[li + 1].attn_norm : c->ln_f, e2)) return -1;
+        }
     }
+    if (join()) return -1;
     *epoch_out = epoch;
     return 0;
 }

@@ -351,7 +351,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
             if (!qa) return set_error("gemm: qkv epilogue needs QkvRopeArgs");
             if (qa->d_model % 256 || N != 3 * qa->d_model || qa->d_model != qa->n_heads * 128)
                 return set_error("gemm: qkv epilogue needs head_dim 128, d_model % 256 == 0, N == 3*d_model");
-            if (qa->pos_map ? (qa->Tq <= 0 || M % qa->Tq) : (M % qa->L)) return set_error("gemm: qkv epilogue needs M == B*L (or B*Tq with a position map)");
+            if (qa->pos_map ? (qa->Tq <= 0 || M % qa->Tq) : (!qa->chunked && (M % qa->L))) return set_error("gemm: qkv epilogue needs M == B*L (or B*Tq with a position map)");
             break;
         default:
             return set_error("gemm: unknown epilogue");
@@ -419,7 +419,7 @@ int gemm_bf16(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
         case EPI_QKVROPE:
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
-            p.pos_map = qa->pos_map; p.Tq = qa->Tq;
+            p.pos_map = qa->pos_map; p.Tq = qa->Tq; p.row0 = qa->row0;
             return launch_gemm<EPI_QKVROPE, 256>(tmA, tmB, p, grid, stream);
         default:
             return set_error("gemm: unknown epilogue");

@@ -297,7 +297,7 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
         case EPI_QKVROPE:
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
-            p.pos_map = qa->pos_map; p.Tq = qa->Tq;
+            p.pos_map = qa->pos_map; p.Tq = qa->Tq; p.row0 = qa->row0;
             return launch_pair<EPI_QKVROPE, 256>(tmA, tmB, tmBh, p, stream);
         default:
             return set_error("gemm_pair: unknown epilogue");

@@ -24,6 +24,7 @@ struct GemmParams {
     // nullptr: row r is token r % L of batch row r / L
     const int* pos_map;
     int Tq;
+    int row0;  // QKVROPE: sequence index of GEMM row 0 (row-chunked launches); q / k are addressed relative to it, positions and V^T absolutely
     // split-K tail (gemm.cu): the last `sk_tail` tiles (a partial wave) are split along K into `sk_splits` (<= 8) units of
     // `sk_kb_per` k-blocks; partial accumulators meet in `sk_ws` (fp32, [tail][splits][BN/4][128] float4: column-group major,
     // tile row minor, so that both the publishing threads (thread = row) and the finishing threads (consecutive threads =
@@ -188,8 +189,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                     b = row_ok ? row / p.Tq : 0;
                     pos = row_ok ? p.pos_map[row] : 0;
                 } else {
-                    b = row_ok ? row / p.L : 0;
-                    pos = row_ok ? row - b * p.L : 0;
+                    b = row_ok ? (row + p.row0) / p.L : 0;
+                    pos = row_ok ? (row + p.row0) - b * p.L : 0;
                 }
                 if (region < 2) {
                     const size_t drow = (region == 0 || !p.pos_map) ? (size_t)row : (size_t)b * p.L + pos;  // k rows go to their sequence position
@@ -374,7 +375,7 @@ __device__ __forceinline__ void sk_finish(const GemmParams& p, const float4* __r
                 const int col4[4] = {head * 32 + 2 * gg, head * 32 + 2 * gg + 1, head * 32 + 16 + 2 * gg, head * 32 + 16 + 2 * gg + 1};
                 float4 a[4];
                 sk_sum<BN, 4>(tile_ws, S, rit, col4, a);
-                const int pos = row % p.L;
+                const int pos = (row + p.row0) % p.L;
                 const float4* c4 = reinterpret_cast<const float4*>(p.cos_tab + (size_t)pos * 64 + 8 * gg);
                 const float4* s4 = reinterpret_cast<const float4*>(p.sin_tab + (size_t)pos * 64 + 8 * gg);
                 const float4 c0 = c4[0], c1 = c4[1], s0 = s4[0], s1 = s4[1];
@@ -404,7 +405,7 @@ __device__ __forceinline__ void sk_finish(const GemmParams& p, const float4* __r
                 const int col4[2] = {2 * g, 2 * g + 1};
                 float4 a[2];
                 sk_sum<BN, 2>(tile_ws, S, rit, col4, a);
-                const int b = row / p.L, pos = row - b * p.L;
+                const int b = (row + p.row0) / p.L, pos = (row + p.row0) - b * p.L;
                 const int n = n0 - 2 * p.d_model + 8 * g;
                 const int head = n >> 7, d0 = n & 127;
                 __nv_bfloat16* dst = p.vt + ((size_t)(b * p.n_heads + head) * 128 + d0) * p.Lpad + pos;

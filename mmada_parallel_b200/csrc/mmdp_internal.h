@@ -103,6 +103,8 @@ struct QkvRopeArgs {
     int L, Lpad, d_model, n_heads;
     const int* pos_map = nullptr;  // token-cache forward: compact row r = token pos_map[r] of batch row r / Tq (k, v^T scattered to it)
     int Tq = 0;
+    int chunked = 0;  // 1: the launch covers a row range of the [B*L] sequence (M need not be a multiple of L)
+    int row0 = 0;  // GEMM row r is token row0 + r of the flattened [B*L] sequence (row-chunked tensor-parallel forward); q / k point at that row
 };
 
 // EPI_F32 only: push the fp32 partial rows to their owners' receive buffers instead of storing them to C (tensor parallel)

@@ -80,6 +80,17 @@ def row_partition(M: int, tp: int, rank: int):
     return r0, max(0, min(R, M - r0))
 
 
+def chunk_split(M: int) -> List[int]:
+    """Row chunks of the pipelined tensor-parallel forward: [M] for short sequences, else two chunks, the first a multiple of
+    256 rows (whole CTA-pair GEMM tiles) closest to M / 2 from above. With two chunks the attn_out / MLP part of a layer runs as
+    two independent chains on two streams: one chunk's NVLink traffic overlaps the other chunk's GEMMs (csrc/api.cu,
+    mmdp_tp_forward)."""
+    if M < 1024:
+        return [M]
+    r0 = (M // 2 + 255) // 256 * 256
+    return [r0, M - r0]
+
+
 class _DeviceArray:
     """Zero-copy torch view of a raw device allocation (a cudaMalloc made by libmmdp for IPC export)."""
 
@@ -126,13 +137,16 @@ class TensorParallelLLaDA:
 
     def __init__(self, config, state_dict: Dict[str, torch.Tensor], tp_rank: int, tp_size: int, group=None,
                  max_seq_len: Optional[int] = None, max_batch: int = 1, device: str = "cuda:0", text_vocab_size: int = 126356,
-                 codebook_size: int = 8192, collective: str = "p2p"):
+                 codebook_size: int = 8192, collective: str = "p2p", chunks: int = 2):
         if not torch.cuda.is_available():
             raise _lib.MmdpError("mmada_parallel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if collective not in ("p2p", "nccl"):
             raise ValueError("collective must be 'p2p' (NVLink peer-memory kernel) or 'nccl' (all-reduce baseline)")
         self.config, self.group, self.rank, self.tp = config, group, tp_rank, tp_size
         self.collective = collective if tp_size > 1 else "nccl"
+        if chunks not in (1, 2):
+            raise ValueError("chunks must be 1 or 2")
+        self.chunks = chunks
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         g = lambda k, dflt=None: getattr(config, k, dflt)
@@ -165,13 +179,20 @@ class TensorParallelLLaDA:
         if self.collective == "p2p":
             if M < tp_size:
                 raise ValueError("the workspace must hold at least one row per rank")
-            # receive buffers [tp][R][d] fp32 (slot r <- rank r's partial rows for the rows this rank owns), used alternately
-            self._recv = [_SharedBuffer(tp_size * rows_per_rank(M, tp_size) * d * 4, tp_rank, tp_size, group) for _ in range(2)]
+            # per row chunk (see chunk_split): receive buffers [tp][R][d] fp32 (slot r <- rank r's partial rows for the rows this
+            # rank owns), used alternately; flags; this rank's rows of the residual stream. Chunk 0 is sized for the whole
+            # workspace (a short sequence runs as one chunk), chunk 1 for half of it.
+            self._chunk_state = []
+            for ci in range(self.chunks):
+                rows = M if ci == 0 else (M + 1) // 2          # chunk 1 never holds more than half of the rows (chunk_split)
+                R = rows_per_rank(rows, tp_size)
+                st = {"recv": [_SharedBuffer(tp_size * R * d * 4, tp_rank, tp_size, group) for _ in range(2)],
+                      "flags": _SharedBuffer(2 * 8 * 4, tp_rank, tp_size, group),
+                      "x": torch.empty((R, d), **bf), "done": torch.zeros(1, dtype=torch.int32, device=self.device)}
+                self._chunk_state.append(st)
             self._xn = _SharedBuffer(M * d * 2, tp_rank, tp_size, group)
-            self._flags = _SharedBuffer(2 * 8 * 4, tp_rank, tp_size, group)
             self.xn = torch.as_tensor(_DeviceArray(self._xn.own, M * d, "<u2"), device=self.device).view(torch.bfloat16).view(M, d)
-            self.x = torch.empty((rows_per_rank(M, tp_size), d), **bf)                            # this rank's rows of the residual stream
-            self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.x = self._chunk_state[0]["x"]
             self._epoch = 0
             torch.cuda.synchronize()
             dist.barrier(group=group)  # every rank has mapped every buffer before the first peer access
@@ -181,7 +202,10 @@ class TensorParallelLLaDA:
             self.part = torch.empty((M, d), dtype=torch.float32, device=self.device)
 
     def __del__(self):
-        for b in getattr(self, "_recv", []) + [getattr(self, "_xn", None), getattr(self, "_flags", None)]:
+        shared = [getattr(self, "_xn", None)]
+        for st in getattr(self, "_chunk_state", []):
+            shared += st["recv"] + [st["flags"]]
+        for b in shared:
             if b is not None:
                 try:
                     b.close()
@@ -249,12 +273,17 @@ class TensorParallelLLaDA:
         c.wte, c.ln_f, c.vocab = w["wte"].data_ptr(), w["ln_f"].data_ptr(), w["wte"].shape[0]
         c.cos_tab, c.sin_tab = self.cos.data_ptr(), self.sin.data_ptr()
         c.q, c.k, c.att, c.h, c.vt = self.q.data_ptr(), self.k.data_ptr(), self.att.data_ptr(), self.h.data_ptr(), self.vt.data_ptr()
-        c.x_shard = self.x.data_ptr()
-        c.recv[0] = C.cast(self._recv[0].array, C.POINTER(C.c_void_p))
-        c.recv[1] = C.cast(self._recv[1].array, C.POINTER(C.c_void_p))
         c.xn = C.cast(self._xn.array, C.POINTER(C.c_void_p))
-        c.flags = C.cast(self._flags.array, C.POINTER(C.c_void_p))
-        c.done_counter = self._done.data_ptr()
+        split = chunk_split(B * L) if self.chunks == 2 else [B * L]
+        c.n_chunks = len(split)
+        c.chunk_rows0 = split[0]
+        for ci in range(len(split)):
+            st = self._chunk_state[ci]
+            c.chunk[ci].x_shard = st["x"].data_ptr()
+            c.chunk[ci].recv[0] = C.cast(st["recv"][0].array, C.POINTER(C.c_void_p))
+            c.chunk[ci].recv[1] = C.cast(st["recv"][1].array, C.POINTER(C.c_void_p))
+            c.chunk[ci].flags = C.cast(st["flags"].array, C.POINTER(C.c_void_p))
+            c.chunk[ci].done_counter = st["done"].data_ptr()
         self._ctx, self._ctx_layers, self._ctx_key = c, layers, key   # (keep the layer array alive)
         return c
 
@@ -270,8 +299,9 @@ class TensorParallelLLaDA:
             self._vt_key = (B, Lpad, L)
         wte = self.w["wte"]
         if self.collective == "p2p":
-            if row_partition(M, self.tp, self.tp - 1)[1] < 1:
-                raise _lib.MmdpError(f"TensorParallelLLaDA: {M} tokens cannot be split over {self.tp} ranks with at least one row each")
+            for rows in (chunk_split(M) if self.chunks == 2 else [M]):
+                if row_partition(rows, self.tp, self.tp - 1)[1] < 1:
+                    raise _lib.MmdpError(f"TensorParallelLLaDA: {rows} rows cannot be split over {self.tp} ranks with at least one row each")
             # the whole body is one native call (a Python loop of ~10 launches per layer left a TP=8 rank CPU-bound)
             out = C.c_uint32(0)
             check(lib.mmdp_tp_forward(C.byref(self._native_ctx(B, L)), ptr(ids), B, L, self._epoch, C.byref(out), s))
