@@ -13,8 +13,8 @@
 // i.e. reduce-scatter(fp32) + residual + norm + all-gather(bf16): 0.75x the bytes of the fp32 all-reduce it replaces, no
 // separate residual / RMSNorm launches, and the summation order is the same on every rank and in every run.
 // Synchronisation is a flag per (phase, source rank) in each rank's memory, written by the peers with system-scope
-// release stores: phase 0 "my partial sums are complete" (sent when this kernel starts, i.e. after the producing GEMM in
-// stream order), phase 1 "my rows of xn have landed in your buffer" (sent by the last CTA). The consumer of xn waits for
+// release stores: phase 0 "my partial sums are complete" (sent by tp_rendezvous_kernel, a one-CTA launch that follows the
+// producing GEMM in stream order and waits for everybody's), phase 1 "my rows of xn have landed in your buffer" (sent by the last CTA). The consumer of xn waits for
 // phase 1 of all ranks in tp_wait_kernel. Flags carry a monotonically increasing epoch, so they never need resetting.
 // Buffer reuse is safe with TWO partial buffers used alternately (a rank can only overwrite a partial buffer two
 // collectives later, after it has itself passed the next phase-0 barrier, which every peer joins only after its reads).
@@ -72,15 +72,10 @@ __device__ __forceinline__ void tp_wait_flags(const uint32_t* flags_local, int p
 template <int NV>  // d <= 2048 * NV columns (d % 8 == 0): every thread owns up to NV groups of 8 consecutive columns
 __global__ void __launch_bounds__(kTpThreads) tp_reduce_norm_kernel(TpReduceArgs a) {
     const int tid = threadIdx.x;
-    uint32_t* flags_local = a.flags[a.my_rank];
-    // programmatic dependent launch: this grid may start under the tail of the GEMM that pushes this rank's partial rows; the
-    // "my pushes are complete" signal below must not be sent before that GEMM has completed
+    // the phase-0 rendezvous (every rank's partial sums are complete) has been passed by tp_rendezvous_kernel, the previous
+    // launch in this stream: this grid never spins
     pdl_launch_dependents();
     pdl_wait();
-    // phase 0: tell every rank that this rank has reached this collective - its partial sums are complete and it no longer
-    // reads the activation buffer the peers are about to overwrite - then wait for everybody's
-    if (blockIdx.x == 0 && tid < a.n_ranks) st_release_sys(a.flags[tid] + 0 * kTpMaxRanks + a.my_rank, a.epoch);
-    tp_wait_flags(flags_local, 0, a.n_ranks, a.epoch);
     const int lrow = blockIdx.x;
     const size_t grow = (size_t)(a.row0 + lrow) * a.d;
     __nv_bfloat16* xrow = a.x_shard + (size_t)lrow * a.d;
@@ -168,10 +163,26 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_norm_kernel(TpReduceArgs
     if (s_last && tid < a.n_ranks) st_release_sys(a.flags[tid] + 1 * kTpMaxRanks + a.my_rank, a.epoch);
 }
 
-__global__ void tp_wait_kernel(const uint32_t* flags_local, int phase, int n_ranks, uint32_t epoch) {
+// Phase 0 of a collective, ONE small CTA: tell every rank that this rank has reached the collective - its partial sums are
+// complete (this kernel follows the producing GEMM in stream order) and it no longer reads the activation buffer the peers are
+// about to overwrite - then wait for everybody's. The rendezvous is a kernel of its own so that nothing that spins on a
+// peer holds more than 32 threads of this GPU: with two row chunks in flight, a 600-CTA reduce grid spinning on chunk A's
+// flags filled the register files and kept chunk B's GEMM - which the PEER's chunk-B wait depended on - from starting
+// (cross-rank deadlock, found by the flag-wait timeout at TP=2).
+struct TpFlagPtrs { uint32_t* f[kTpMaxRanks]; };
+__global__ void tp_rendezvous_kernel(TpFlagPtrs flags, int my_rank, int n_ranks, uint32_t epoch) {
+    pdl_wait();
+    if ((int)threadIdx.x < n_ranks) st_release_sys(flags.f[threadIdx.x] + 0 * kTpMaxRanks + my_rank, epoch);
+    tp_wait_flags(flags.f[my_rank], 0, n_ranks, epoch);
+    // only now may the dependent grid be scheduled: launched early it would sit at its griddepcontrol.wait holding registers
+    // and shared memory on every SM while this CTA spins on the peers (the same starvation as a spinning grid)
     pdl_launch_dependents();
+}
+
+__global__ void tp_wait_kernel(const uint32_t* flags_local, int phase, int n_ranks, uint32_t epoch) {
     pdl_wait();
     tp_wait_flags(flags_local, phase, n_ranks, epoch);
+    pdl_launch_dependents();  // after the wait, see tp_rendezvous_kernel
 }
 
 int tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16_t* const* xn, uint32_t* const* flags, int n_ranks,
@@ -194,6 +205,12 @@ int tp_reduce_norm(const float* recv_local, int rows_per_rank, int n_src, uint16
     a.row0 = row0; a.nrows = nrows; a.d = d; a.eps = eps; a.epoch = epoch; a.done_counter = done_counter;
     const bool pdl = pdl_mode() != 0;
     cudaError_t e;
+    {
+        TpFlagPtrs fp{};
+        for (int r = 0; r < n_ranks; ++r) fp.f[r] = flags[r];
+        LaunchScope ls0(LK_ROW, 0.0, stream);
+        MMDP_CUDA(launch_ex(tp_rendezvous_kernel, dim3(1), dim3(32), 0, stream, pdl, false, fp, my_rank, n_ranks, epoch));
+    }
     {
     // bytes this rank moves: reads n_src fp32 rows + x, writes x + n_ranks bf16 rows
     LaunchScope ls(LK_ROW, (double)nrows * d * (4.0 * n_src + 4.0 + 2.0 * n_ranks), stream);
