@@ -583,10 +583,12 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
         dist.broadcast(ref, src=0)
         same = torch.tensor([1 if torch.equal(mine, ref) else 0], device=device)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        # the same model with ONE row chunk (no second stream: collective traffic and GEMMs of a layer strictly alternate), one sample
+        # the same model with the OTHER row-chunk schedule (1 chunk: collective traffic and GEMMs of a layer strictly alternate;
+        # 2 chunks on two streams: one chunk's NVLink traffic under the other's GEMMs), one sample
         one_chunk_tok_s = None
-        if getattr(tp, "chunks", 1) == 2:
-            tp.chunks, tp._ctx_key = 1, None
+        main_chunks = int(getattr(tp, "chunks", 1))
+        if True:
+            tp.chunks, tp._ctx_key = (1 if main_chunks == 2 else 2), None
             dist.barrier()
             torch.cuda.synchronize()
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -621,9 +623,9 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
         nccl_tok_s = f"error: {type(e).__name__}: {e}"[:200]
     v = steps * TOKENS_PER_SAMPLE / (ms / 1e3)
     return {"metric": "denoised_tokens_per_sec", "value": v, "nccl_allreduce_baseline_tokens_per_s": nccl_tok_s,
-            "one_row_chunk_tokens_per_s": one_chunk_tok_s,
+            "row_chunks": main_chunks, "other_row_chunk_schedule": {"row_chunks": 1 if main_chunks == 2 else 2, "tokens_per_s": one_chunk_tok_s},
             "collective": "GEMM-fused reduce-scatter + reduce/residual/RMSNorm/broadcast kernel over NVLink peer memory (csrc/tp_collective.cu); "
-                          "two row chunks on two streams, one chunk's NVLink traffic under the other's GEMMs",
+                          "row_chunks = 2: two row chunks on two streams, one chunk's NVLink traffic under the other's GEMMs (default from TP=4)",
             "kernel_breakdown_one_sample_ms": {"gemm_incl_scatter_push": tp_prof["gemm"][0], "attention": tp_prof["attention"][0],
                                                "reduce_norm_broadcast_and_waits": tp_prof["row"][0], "sampling": tp_prof["sampling"][0]}, "unit": "tokens/s", "n_gpus": world, "steps": steps, "scaling": "strong",
             "ms_per_step": ms / steps, "config": {"workload": "BASELINE configs[3]: ONE prompt, tensor-parallel attention/MLP/LM head over the GPUs",

@@ -137,16 +137,22 @@ class TensorParallelLLaDA:
 
     def __init__(self, config, state_dict: Dict[str, torch.Tensor], tp_rank: int, tp_size: int, group=None,
                  max_seq_len: Optional[int] = None, max_batch: int = 1, device: str = "cuda:0", text_vocab_size: int = 126356,
-                 codebook_size: int = 8192, collective: str = "p2p", chunks: int = 2):
+                 codebook_size: int = 8192, collective: str = "p2p", chunks: Optional[int] = None):
         if not torch.cuda.is_available():
             raise _lib.MmdpError("mmada_parallel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if collective not in ("p2p", "nccl"):
             raise ValueError("collective must be 'p2p' (NVLink peer-memory kernel) or 'nccl' (all-reduce baseline)")
         self.config, self.group, self.rank, self.tp = config, group, tp_rank, tp_size
         self.collective = collective if tp_size > 1 else "nccl"
+        if chunks is None:
+            # measured (bench.py `tp` record): at TP=2 the NVLink traffic is short against the GEMMs and two half-size chains lose 5 %
+            # (306 vs 323 tokens/s); from TP=4 on the collectives are wire-bound (fp32 partial rows: 7/8 of 39.5 MB out of every
+            # GPU per collective at TP=8) and worth hiding under the other chunk's GEMMs
+            chunks = 2 if tp_size >= 4 else 1
         if chunks not in (1, 2):
             raise ValueError("chunks must be 1 or 2")
         self.chunks = chunks
+        self._alloc_chunks = 2  # buffers for both schedules (chunk 1: half of the workspace rows)
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         g = lambda k, dflt=None: getattr(config, k, dflt)
@@ -183,7 +189,7 @@ class TensorParallelLLaDA:
             # rank owns), used alternately; flags; this rank's rows of the residual stream. Chunk 0 is sized for the whole
             # workspace (a short sequence runs as one chunk), chunk 1 for half of it.
             self._chunk_state = []
-            for ci in range(self.chunks):
+            for ci in range(self._alloc_chunks):
                 rows = M if ci == 0 else (M + 1) // 2          # chunk 1 never holds more than half of the rows (chunk_split)
                 R = rows_per_rank(rows, tp_size)
                 st = {"recv": [_SharedBuffer(tp_size * R * d * 4, tp_rank, tp_size, group) for _ in range(2)],

@@ -5,6 +5,6 @@ tail -12 gpurun_out/r2_pytest15_tp.log | cut -c1-300; tail -3 gpurun_out/r2_benc
 import json
 try:
     d=json.loads([l for l in open('gpurun_out/r2_bench_n2b.json') if l.startswith('{')][-1]); t=d['tp']
-    print(d['value'], t['value'], t['one_row_chunk_tokens_per_s'], t['nccl_allreduce_baseline_tokens_per_s'], t['tp_parity']['ok'], t['tp_parity']['ranks_final_ids_identical'], t['kernel_breakdown_one_sample_ms'])
+    print(d['value'], t['value'], t['row_chunks'], t['other_row_chunk_schedule'], t['nccl_allreduce_baseline_tokens_per_s'], t['tp_parity']['ok'], t['tp_parity']['ranks_final_ids_identical'], t['kernel_breakdown_one_sample_ms'])
 except Exception as e: print('ERR', e)
 PY
