@@ -145,10 +145,10 @@ class TensorParallelLLaDA:
         self.config, self.group, self.rank, self.tp = config, group, tp_rank, tp_size
         self.collective = collective if tp_size > 1 else "nccl"
         if chunks is None:
-            # measured (bench.py `tp` record): at TP=2 the NVLink traffic is short against the GEMMs and two half-size chains lose 5 %
-            # (306 vs 323 tokens/s); from TP=4 on the collectives are wire-bound (fp32 partial rows: 7/8 of 39.5 MB out of every
-            # GPU per collective at TP=8) and worth hiding under the other chunk's GEMMs
-            chunks = 2 if tp_size >= 4 else 1
+            # measured (bench.py `tp` record, profiles/r02): two half-size chains on two streams LOSE 5 % against one chunk at both
+            # ends of the range - 306 vs 323 tokens/s at TP=2, 510 vs 538 at TP=8: the half-size GEMMs and the doubled launch
+            # count cost more than the NVLink time they hide. The schedule stays available (chunks=2, bitwise identical results).
+            chunks = 1
         if chunks not in (1, 2):
             raise ValueError("chunks must be 1 or 2")
         self.chunks = chunks
