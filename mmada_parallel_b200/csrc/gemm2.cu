@@ -82,7 +82,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmBh, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmAh, const GemmParams p) {
     constexpr int kStages = PairCfg<BN>::kStages;
     constexpr int kStageBytes = PairCfg<BN>::kStageBytes;
     static_assert(EPI == EPI_PLAIN || EPI == EPI_RESID || EPI == EPI_F32 || BN == 256, "fused QKV / SwiGLU epilogues need 256-wide tiles");
@@ -137,6 +137,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr bool kCanSplit = PairCfg<BN>::template can_split<EPI>();
     const int t_full = kCanSplit ? num_tiles - p.nsplit_tail : num_tiles;
     const int num_units = t_full + 2 * (num_tiles - t_full);
+    // Half-M units (SwiGLU epilogue, p.mtail): the units of n-tile g are its num_m - 1 whole 256-row tiles plus ONE 128-row unit for
+    // the last m-block (M % 256 <= 128), which the pair computes with M = 128 MMAs (64 rows per CTA) in half the cycles. The half
+    // unit sits at position (g / mt_period) % num_m of the group so that unit % num_clusters spreads them over all clusters.
+    constexpr bool kMTail = EPI == EPI_SWIGLU && BN == 256;
+    auto decode = [&](int unit, int& m_blk, int& n_blk, bool& mhalf) {
+        n_blk = unit / num_m;
+        const int o = unit - n_blk * num_m;
+        mhalf = false;
+        m_blk = o;
+        if (kMTail && p.mtail) {
+            const int sp = (n_blk / p.mt_period) % num_m;
+            mhalf = o == sp;
+            m_blk = mhalf ? num_m - 1 : (o < sp ? o : o - 1);
+        }
+    };
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -146,11 +161,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
                 const bool half = kCanSplit && unit >= t_full;
                 const int tile = half ? t_full + ((unit - t_full) >> 1) : unit;
-                const int m_blk = tile % num_m, n_blk = tile / num_m;
-                const int row0 = m_blk * 2 * P_BM + (int)rank * P_BM;       // this CTA's 128 rows of A
-                // this CTA's half of the W rows of the unit (BN rows, or BN/2 for a half unit)
+                int m_blk, n_blk;
+                bool mhalf;
+                decode(tile, m_blk, n_blk, mhalf);
+                // this CTA's rows of A: 128 of the 256-row tile, or 64 of the 128-row half-M unit
+                const int row0 = mhalf ? m_blk * 2 * P_BM + (int)rank * (P_BM / 2) : m_blk * 2 * P_BM + (int)rank * P_BM;
+                // this CTA's half of the W rows of the unit (BN rows, or BN/2 for a half-N unit)
                 const int wrow0 = half ? n_blk * BN + ((unit - t_full) & 1) * (BN / 2) + (int)rank * (BN / 4) : n_blk * BN + (int)rank * (BN / 2);
-                const uint32_t tx = half ? 2 * (kPABytes + PairCfg<BN>::kBHalfBytes / 2) : 2 * kStageBytes;  // bytes of both CTAs
+                const uint32_t tx = half ? 2 * (kPABytes + PairCfg<BN>::kBHalfBytes / 2)
+                                         : (mhalf ? 2 * (kPABytes / 2 + PairCfg<BN>::kBHalfBytes) : 2 * kStageBytes);  // bytes of both CTAs
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[s]), 0);
@@ -160,8 +179,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         mbar_arrive_cluster(leader_full);
                     }
                     uint8_t* sa = smem + s * kStageBytes;
-                    tma_load_2d_pair(sa, &tmA, leader_full, kb * P_BK, row0);
-                    tma_load_2d_pair(sa + kPABytes, half ? &tmBh : &tmB, leader_full, kb * P_BK, wrow0);
+                    if (kMTail && mhalf) {
+                        // half-M unit: 64 rows of A; W rows so that the 128 accumulator columns one TMEM lane half holds are
+                        // [64 gate | 64 up] of the SAME 64 outputs (CTA r: gate rows n_blk*256 + 64r.., up rows n_blk*256 + 128 + 64r..)
+                        tma_load_2d_pair(sa, &tmAh, leader_full, kb * P_BK, row0);
+                        tma_load_2d_pair(sa + kPABytes, &tmBh, leader_full, kb * P_BK, n_blk * BN + (int)rank * (BN / 4));
+                        tma_load_2d_pair(sa + kPABytes + PairCfg<BN>::kBHalfBytes / 2, &tmBh, leader_full, kb * P_BK, n_blk * BN + BN / 2 + (int)rank * (BN / 4));
+                    } else {
+                        tma_load_2d_pair(sa, &tmA, leader_full, kb * P_BK, row0);
+                        tma_load_2d_pair(sa + kPABytes, half ? &tmBh : &tmB, leader_full, kb * P_BK, wrow0);
+                    }
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
@@ -176,8 +203,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
+            constexpr uint32_t idesc_mhalf = umma_idesc_bf16(P_BM, BN);  // cta_group::2, M = 128: 64 rows per CTA
             for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-                const uint32_t idesc = (kCanSplit && unit >= t_full) ? idesc_half : idesc_whole;
+                uint32_t idesc = (kCanSplit && unit >= t_full) ? idesc_half : idesc_whole;
+                if (kMTail && p.mtail) {
+                    int m_blk, n_blk;
+                    bool mhalf;
+                    decode(unit, m_blk, n_blk, mhalf);
+                    if (mhalf) idesc = idesc_mhalf;
+                }
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -206,12 +240,29 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
             const bool half = kCanSplit && unit >= t_full;
             const int tile = half ? t_full + ((unit - t_full) >> 1) : unit;
-            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            int m_blk, n_blk;
+            bool mhalf;
+            decode(tile, m_blk, n_blk, mhalf);
             mbar_wait(&tmem_full[as], aph);
             tcgen05_fence_after();
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+            if (kMTail && mhalf) {
+                // M = 128 pair MMA: this CTA's 64 rows x 256 columns sit in TMEM as lanes 0..63 x columns [0,128) | lanes 64..127 x
+                // columns [128,256), 128 TMEM columns. With the W rows ordered as above a lane half holds [64 gate | 64 up] of 64 outputs.
+                const int ln = ew * 32 + lane, hq = ln >> 6;
+                const int row = m_blk * 2 * P_BM + (int)rank * (P_BM / 2) + (ln & 63);
+                const bool row_ok = row < p.M;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(tbase + c * 32, g);
+                    tmem_ld_32x32b_x32(tbase + 64 + c * 32, u);
+                    tmem_ld_wait();
+                    swiglu_store32(p, g, u, row, row_ok, n_blk * 128 + hq * 64 + c * 32);
+                }
+            } else {
             const int row = m_blk * 2 * P_BM + (int)rank * P_BM + ew * 32 + lane;
             const bool row_ok = row < p.M;
-            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
             if constexpr (kCanSplit) {
                 if (half)
                     gemm_epilogue_tile<EPI, BN / 2>(p, tbase, row, row_ok, 2 * n_blk + ((unit - t_full) & 1), scat_stage + ew * kScatStageFloats);
@@ -219,6 +270,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
             } else {
                 gemm_epilogue_tile<EPI, BN>(p, tbase, row, row_ok, n_blk, scat_stage + ew * kScatStageFloats);
+            }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -239,7 +291,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int EPI, int BN>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, GemmParams& p, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& tmAh, GemmParams& p, cudaStream_t stream) {
     static unsigned long long attr_set = 0;  // bit per device
     int dev = 0;
     MMDP_CUDA(cudaGetDevice(&dev));
@@ -254,9 +306,17 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const int tail = num_tiles % pairs;
     p.nsplit_tail = (PairCfg<BN>::template can_split<EPI>() && opt(OPT_GEMM_NSPLIT_TAIL) && num_tiles > pairs && tail > 0 &&
                      2 * tail <= pairs && p.N % BN == 0) ? tail : 0;
+    // half-M units for the last m-block (SwiGLU): at most 128 valid rows in it, more than one m-block, whole 256-wide n-tiles
+    const int num_m = (p.M + 2 * P_BM - 1) / (2 * P_BM), m_rem = p.M - (num_m - 1) * 2 * P_BM;
+    p.mtail = (EPI == EPI_SWIGLU && BN == 256 && opt(OPT_GEMM_MTAIL) && num_m >= 2 && m_rem <= P_BM && p.N % BN == 0 && num_tiles > pairs) ? 1 : 0;
+    if (p.mtail) {
+        int a = num_m, b = pairs;  // period of (num_m * g) mod pairs
+        while (b) { const int t = a % b; a = b; b = t; }
+        p.mt_period = pairs / a;
+    }
     LaunchScope ls(LK_GEMM, 2.0 * p.M * (double)p.N * p.K, stream);
     MMDP_CUDA(launch_ex(gemm_pair_kernel<EPI, BN>, dim3(grid), dim3(kPairThreads), PairCfg<BN>::kSmem, stream, pdl_mode() != 0, false, tmA, tmB,
-                        p.nsplit_tail ? tmBh : tmB, p));
+                        (p.nsplit_tail || p.mtail) ? tmBh : tmB, p.mtail ? tmAh : tmA, p));
     return 0;
 }
 
@@ -284,21 +344,23 @@ int gemm_bf16_pair(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16
     if (make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, P_BM, P_BK)) return -1;
     if (make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn / 2, P_BK)) return -1;
     CUtensorMap tmBh = tmB;  // box of bn / 4 W rows: one CTA's share of a half unit (tail N-split)
-    if (bn == 256 && epi != EPI_SWIGLU && epi != EPI_F32 && make_tmap_2d_bf16(&tmBh, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn / 4, P_BK)) return -1;
+    if (bn == 256 && epi != EPI_F32 && make_tmap_2d_bf16(&tmBh, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, bn / 4, P_BK)) return -1;
+    CUtensorMap tmAh = tmA;  // box of 64 A rows: one CTA's share of a half-M unit
+    if (epi == EPI_SWIGLU && make_tmap_2d_bf16(&tmAh, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, P_BM / 2, P_BK)) return -1;
     switch (epi) {
         case EPI_PLAIN:
-            return bn == 192 ? launch_pair<EPI_PLAIN, 192>(tmA, tmB, tmBh, p, stream) : launch_pair<EPI_PLAIN, 256>(tmA, tmB, tmBh, p, stream);
+            return bn == 192 ? launch_pair<EPI_PLAIN, 192>(tmA, tmB, tmBh, tmAh, p, stream) : launch_pair<EPI_PLAIN, 256>(tmA, tmB, tmBh, tmAh, p, stream);
         case EPI_RESID:
-            return bn == 192 ? launch_pair<EPI_RESID, 192>(tmA, tmB, tmBh, p, stream) : launch_pair<EPI_RESID, 256>(tmA, tmB, tmBh, p, stream);
+            return bn == 192 ? launch_pair<EPI_RESID, 192>(tmA, tmB, tmBh, tmAh, p, stream) : launch_pair<EPI_RESID, 256>(tmA, tmB, tmBh, tmAh, p, stream);
         case EPI_F32:
-            return bn == 192 ? launch_pair<EPI_F32, 192>(tmA, tmB, tmBh, p, stream) : launch_pair<EPI_F32, 256>(tmA, tmB, tmBh, p, stream);
+            return bn == 192 ? launch_pair<EPI_F32, 192>(tmA, tmB, tmBh, tmAh, p, stream) : launch_pair<EPI_F32, 256>(tmA, tmB, tmBh, tmAh, p, stream);
         case EPI_SWIGLU:
-            return launch_pair<EPI_SWIGLU, 256>(tmA, tmB, tmBh, p, stream);
+            return launch_pair<EPI_SWIGLU, 256>(tmA, tmB, tmBh, tmAh, p, stream);
         case EPI_QKVROPE:
             p.q = qa->q; p.k = qa->k; p.vt = qa->vt; p.cos_tab = qa->cos_tab; p.sin_tab = qa->sin_tab;
             p.L = qa->L; p.Lpad = qa->Lpad; p.d_model = qa->d_model; p.n_heads = qa->n_heads;
             p.pos_map = qa->pos_map; p.Tq = qa->Tq; p.row0 = qa->row0;
-            return launch_pair<EPI_QKVROPE, 256>(tmA, tmB, tmBh, p, stream);
+            return launch_pair<EPI_QKVROPE, 256>(tmA, tmB, tmBh, tmAh, p, stream);
         default:
             return set_error("gemm_pair: unknown epilogue");
     }

@@ -45,6 +45,10 @@ struct GemmParams {
     int group_m;
     // CTA-pair kernel: number of tiles of the partial last wave that are cut into two half-width units (gemm2.cu)
     int nsplit_tail;
+    // CTA-pair kernel, SwiGLU epilogue: M % 256 <= 128 -> the last m-block runs as 128-row "half-M" units (cta_group::2 MMAs with
+    // M = 128, 64 rows per CTA, half the cycles of a 256-row tile). Inside the num_m units of n-tile g the half unit sits at
+    // position (g / mt_period) % num_m so that the round-robin unit -> cluster map hands every cluster its share of them.
+    int mtail, mt_period;
 };
 
 __host__ __device__ __forceinline__ void gemm_tile_coords(int tl, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
@@ -67,6 +71,27 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (i * 8 < ncols_valid) d4[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+    }
+}
+
+// SwiGLU of 32 (gate, up) column pairs of one row, rounding points of modeling_llada.py:962-967, stored as 32 bf16
+__device__ __forceinline__ void swiglu_store32(const GemmParams& p, const uint32_t (&g)[32], const uint32_t (&u)[32], int row, bool row_ok, int col0) {
+    const int nvalid = p.N / 2 - col0;
+    if (row_ok && nvalid > 0) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float o[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float gg = bf16_round(__uint_as_float(g[2 * i + h]));
+                float uu = bf16_round(__uint_as_float(u[2 * i + h]));
+                float s = bf16_round(__fdiv_rn(gg, __fadd_rn(1.0f, expf(-gg))));  // silu -> bf16
+                o[h] = __fmul_rn(s, uu);
+            }
+            pk[i] = pack_bf16x2(o[0], o[1]);
+        }
+        store_bf16x32(p.C + (size_t)row * p.ldc + col0, pk, nvalid);
     }
 }
 
@@ -163,24 +188,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                     tmem_ld_32x32b_x32(tbase + c * 32, g);
                     tmem_ld_32x32b_x32(tbase + 128 + c * 32, u);
                     tmem_ld_wait();
-                    const int col0 = n_blk * 128 + c * 32;
-                    const int nvalid = p.N / 2 - col0;
-                    if (row_ok && nvalid > 0) {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float o[2];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                float gg = bf16_round(__uint_as_float(g[2 * i + h]));
-                                float uu = bf16_round(__uint_as_float(u[2 * i + h]));
-                                float s = bf16_round(__fdiv_rn(gg, __fadd_rn(1.0f, expf(-gg))));  // silu -> bf16
-                                o[h] = __fmul_rn(s, uu);
-                            }
-                            pk[i] = pack_bf16x2(o[0], o[1]);
-                        }
-                        store_bf16x32(p.C + (size_t)row * p.ldc + col0, pk, nvalid);
-                    }
+                    swiglu_store32(p, g, u, row, row_ok, n_blk * 128 + c * 32);
                 }
             } else if constexpr (EPI == EPI_QKVROPE) {
                 const int region = n0 / p.d_model;  // 0 = Q, 1 = K, 2 = V (d_model % 256 == 0 is checked on the host)

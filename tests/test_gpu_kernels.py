@@ -372,3 +372,26 @@ def test_gemm_pair_tail_nsplit_bit_identical(epi, M, N, K):
         _lib.check(_lib.lib.mmdp_set_option(b"gemm_nsplit_tail", 1))
     assert torch.equal(got, ref), epi
     assert torch.equal(got, again)
+
+
+@pytest.mark.parametrize("M,N,K", [(2414, 24576, 4096), (2414, 24576, 320), (1100, 5120, 576), (2432, 6144, 448), (2305, 24576, 256), (2500, 24576, 256)])
+def test_gemm_pair_swiglu_half_m_units_bit_identical(M, N, K):
+    """SwiGLU GEMM of the CTA-pair kernel with the last m-block (M % 256 <= 128) computed as 128-row half-M units (cta_group::2 MMAs
+    with M = 128, 64 rows per CTA, W rows re-ordered so that a TMEM lane half holds [64 gate | 64 up] of the same outputs): the same
+    K loop per element, so the result must equal the 256-row-tile schedule bit for bit. (2500 rows: 196 valid rows in the last
+    block, the path is not taken; 2305: a single valid row in it.)"""
+    from mmada_parallel_b200 import _lib
+    torch.manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    w = bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    try:
+        _lib.check(_lib.lib.mmdp_set_option(b"gemm_mtail", 0))
+        ref = _lib.gemm_bf16(a, w, _lib.EPI_SWIGLU)
+        _lib.check(_lib.lib.mmdp_set_option(b"gemm_mtail", 1))
+        got = _lib.gemm_bf16(a, w, _lib.EPI_SWIGLU)
+        again = _lib.gemm_bf16(a, w, _lib.EPI_SWIGLU)
+    finally:
+        _lib.check(_lib.lib.mmdp_set_option(b"gemm_mtail", 1))
+    assert not torch.isnan(got.float()).any()
+    assert torch.equal(got, ref), f"max |d| {(got.float() - ref.float()).abs().max().item()}"
+    assert torch.equal(got, again)

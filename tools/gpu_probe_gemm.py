@@ -16,9 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "pair": dict(gemm_pair=1, gemm_nsplit_tail=0),
-    "pair_nsplit": dict(gemm_pair=1, gemm_nsplit_tail=1),
-    "single": dict(gemm_pair=0, gemm_nsplit_tail=0),
+    "pair": dict(gemm_pair=1, gemm_nsplit_tail=0, gemm_mtail=0),
+    "pair_nsplit": dict(gemm_pair=1, gemm_nsplit_tail=1, gemm_mtail=0),
+    "pair_all": dict(gemm_pair=1, gemm_nsplit_tail=1, gemm_mtail=1),   # + half-M units (SwiGLU GEMM)
+    "single": dict(gemm_pair=0, gemm_nsplit_tail=0, gemm_mtail=0),
 }
 
 
@@ -74,7 +75,7 @@ def main():
                 rec[v + "_tflops"] = round(flops / med / 1e9, 1)
             out.append(rec)
             print(json.dumps(rec), flush=True)
-    for k, val in dict(gemm_pair=1, gemm_nsplit_tail=1).items():
+    for k, val in dict(gemm_pair=1, gemm_nsplit_tail=1, gemm_mtail=1).items():
         _lib.check(_lib.lib.mmdp_set_option(k.encode(), int(val)))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe_gemm.json"), "w") as f:

@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-BASE = dict(pdl=0, gemm_splitk=1, gemm_l2pf=0, gemm_l2pf_mod=4, attn_split_tail=0, gemm_pair=0, gemm_nsplit_tail=0)
+BASE = dict(pdl=0, gemm_splitk=1, gemm_l2pf=0, gemm_l2pf_mod=4, attn_split_tail=0, gemm_pair=0, gemm_nsplit_tail=0, gemm_mtail=0)
 VARIANTS = {
     "r1": {},                                                         # round-1 configuration
     "cur": dict(pdl=1, gemm_splitk=2, attn_split_tail=1),             # 1-CTA kernel with this round's options
@@ -26,7 +26,8 @@ VARIANTS = {
     "cur_sk0": dict(pdl=1, gemm_splitk=0, attn_split_tail=1),
     "cur_noattn": dict(pdl=1, gemm_splitk=2, attn_split_tail=0),
     "cur_pair": dict(pdl=1, gemm_splitk=2, attn_split_tail=1, gemm_pair=1),
-    "cur_pair_nsplit": dict(pdl=1, gemm_splitk=2, attn_split_tail=1, gemm_pair=1, gemm_nsplit_tail=1),   # current defaults
+    "cur_pair_nsplit": dict(pdl=1, gemm_splitk=2, attn_split_tail=1, gemm_pair=1, gemm_nsplit_tail=1),
+    "cur_all": dict(pdl=1, gemm_splitk=2, attn_split_tail=1, gemm_pair=1, gemm_nsplit_tail=1, gemm_mtail=1),   # current defaults
     "r1_pair": dict(gemm_pair=1),
     "l2pf8": dict(gemm_l2pf=8),
 }
