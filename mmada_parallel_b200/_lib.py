@@ -118,6 +118,7 @@ SIGNATURES = {
     "mmdp_model_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i64, _vp]),
     "mmdp_model_set_rope": (_i, [_vp, _vp, _vp, _i, _vp]),
     "mmdp_model_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mmdp_model_forward_window": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "mmdp_model_forward_cached": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mmdp_model_hidden": (_vp, [_vp]),
     "mmdp_model_error_flags": (_i, [_vp, C.POINTER(C.c_int32), _vp]),

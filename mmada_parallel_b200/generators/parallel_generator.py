@@ -94,6 +94,13 @@ class DenoiseState:
         self.ids = ids_host.to(device, non_blocking=False).clone().contiguous()                       # combined_input_ids (:140)
         self.text_rows = torch.arange(text_start, text_end, dtype=torch.int32, device=device)
         self.pos = torch.tensor(self.pos_list, dtype=torch.int32, device=device)
+        # row windows of the last transformer block (model.forward_rows): only rows whose logits are read need its output. Long
+        # sequences only - short ones are launch-bound and the tiny parity models keep one fixed kernel schedule.
+        img_lo, img_hi = min(self.pos_list), max(self.pos_list) + 1
+        use = ids_host.shape[0] == 1 and ids_host.shape[1] >= 1024
+        self.win_text = (text_start, text_end) if use else None
+        self.win_img = (img_lo, img_hi) if use else None
+        self.win_both = (min(text_start, img_lo), max(text_end, img_hi)) if use else None
         self.use_uncond = (cfg_scale > 0.0 and uncon_text is not None) or (cfg_img > 0.0 and uncon_image is not None)
         self.unc_t_ids = uncon_text.to(device=device, dtype=torch.int64) if uncon_text is not None else None
         self.unc_i_ids = uncon_image.to(device=device, dtype=torch.int64) if uncon_image is not None else None
@@ -118,6 +125,11 @@ class DenoiseState:
         return n
 
 
+def _window(model, win):
+    """forward_rows keyword for the last-block row window, for models that take it (the tensor-parallel model does not)."""
+    return {"row_window": win} if (win is not None and getattr(model, "supports_row_window", False)) else {}
+
+
 def denoise_step(st: DenoiseState, step: int, is_img: bool, k_transfer: int, noise: "_Noise", text_steps: int,
                  temperature: float, text_temperature: float, cfg_scale: float, cfg_img: float, noise_schedule,
                  text_vocab_size: int, codebook_size: int, _trace: Optional[list] = None, text_masks_left: int = 1) -> None:
@@ -129,7 +141,8 @@ def denoise_step(st: DenoiseState, step: int, is_img: bool, k_transfer: int, noi
     model, ids, V, n_text, seq_len = st.model, st.ids, st.model.vocab_rows, st.n_text, st.seq_len
     # ---- conditional forward (:178): text rows x V, and the image rows x codebook window on image steps
     model.forward_rows(ids, rows_a=st.text_rows, out_a=st.text_logits, rows_b=st.pos if is_img else None,
-                       col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.cond_vq if is_img else None)
+                       col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.cond_vq if is_img else None,
+                       **_window(model, st.win_both if is_img else st.win_text))
     # ---- text step (:181-217), guarded like the reference's `.sum() > 0` (:183)
     if text_masks_left > 0:
         un = noise.rand((1, n_text, V))[0] if text_temperature != 0 else None
@@ -147,13 +160,15 @@ def denoise_step(st: DenoiseState, step: int, is_img: bool, k_transfer: int, noi
             st.scratch_ids.copy_(ids)
             if st.unc_t_ids is not None:
                 st.scratch_ids[:, : st.unc_t_ids.shape[1]] = st.unc_t_ids
-            model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_t_vq)
+            model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_t_vq,
+                               **_window(model, st.win_img))
             ua = st.unc_t_vq
         if cfg_img != 0.0:
             st.scratch_ids.copy_(ids)
             if st.unc_i_ids is not None:
                 st.scratch_ids[:, : st.unc_i_ids.shape[1]] = st.unc_i_ids
-            model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_i_vq)
+            model.forward_rows(st.scratch_ids, rows_b=st.pos, col0_b=text_vocab_size, ncols_b=codebook_size, out_b=st.unc_i_vq,
+                               **_window(model, st.win_img))
             ub = st.unc_i_vq
     elif st.zeros_vq is not None:
         # no uncond inputs: the reference mixes against zeros (:277-278)

@@ -224,6 +224,8 @@ class LLaDAForMultiModalGeneration:
         ent["logits"][mask] = part                                                                   # :1409-1411
         return ent["logits"]
 
+    supports_row_window = True   # forward_rows(row_window=...): generators/parallel_generator.py
+
     def raise_device_errors(self) -> None:
         """Reads and clears the sticky device-side error flags of the forwards issued so far (synchronises the stream).
         The kernels never read out of bounds; they flag what torch would have raised for."""
@@ -233,6 +235,8 @@ class LLaDAForMultiModalGeneration:
             raise IndexError("index out of range in self (a token id is outside [0, vocab_size))")
         if flags.value & 2:
             raise IndexError("a logits row index is outside [0, batch * seq_len)")
+        if flags.value & 4:
+            raise IndexError("a logits row index is outside the row window given to forward_rows")
 
     # ------------------------------------------------------------------------------------------------------------
     # forward
@@ -270,9 +274,12 @@ class LLaDAForMultiModalGeneration:
 
     def forward_rows(self, ids: torch.Tensor, rows_a: Optional[torch.Tensor] = None, rows_b: Optional[torch.Tensor] = None,
                      col0_b: int = 0, ncols_b: int = 0, out_a: Optional[torch.Tensor] = None,
-                     out_b: Optional[torch.Tensor] = None):
+                     out_b: Optional[torch.Tensor] = None, row_window: Optional[tuple] = None):
         """One forward over ids [B, L] (cuda int64). rows_* are int32 flattened row indices b*L + pos.
-        Returns (logits_a [n_a, V] or None, logits_b [n_b, ncols_b] or None)."""
+        Returns (logits_a [n_a, V] or None, logits_b [n_b, ncols_b] or None).
+        row_window = (lo, hi), batch 1: every row index lies in [lo, hi) - the last block then computes its attention output and
+        MLP for that row range only (keys / values for all rows): nothing after it mixes rows, the skipped rows are never read.
+        A row outside the window raises IndexError at the next raise_device_errors()."""
         B, L = ids.shape
         n_a = 0 if rows_a is None else rows_a.numel()
         n_b = 0 if rows_b is None else rows_b.numel()
@@ -280,6 +287,7 @@ class LLaDAForMultiModalGeneration:
             out_a = torch.empty((n_a, self.vocab_rows), dtype=torch.bfloat16, device=self.device)
         if n_b and out_b is None:
             out_b = torch.empty((n_b, ncols_b), dtype=torch.bfloat16, device=self.device)
-        check(lib.mmdp_model_forward(self._h, ptr(ids), B, L, None, ptr(rows_a), n_a, ptr(out_a) if n_a else None,
-                                     ptr(rows_b), n_b, col0_b, ncols_b, ptr(out_b) if n_b else None, stream_ptr()))
+        lo, hi = (int(row_window[0]), int(row_window[1])) if (row_window is not None and B == 1) else (0, 0)
+        check(lib.mmdp_model_forward_window(self._h, ptr(ids), B, L, ptr(rows_a), n_a, ptr(out_a) if n_a else None,
+                                            ptr(rows_b), n_b, col0_b, ncols_b, ptr(out_b) if n_b else None, lo, hi, stream_ptr()))
         return (out_a if n_a else None), (out_b if n_b else None)

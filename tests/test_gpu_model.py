@@ -210,6 +210,38 @@ def test_full_size_properties():
         _lib.check(_lib.lib.mmdp_set_option(b"attn_split_tail", 1))
     assert torch.equal(b2[:256], b0) and torch.equal(b2[256:], b1), "batch rows must be independent"
     assert torch.isfinite(a2.float()).all() and a2.float().abs().max() > 0.1
+    # Row window of the last block (forward_rows(row_window=...)): only the rows that are read get its attention output and MLP.
+    # The GEMM rows are bit-identical whatever the launch's M is; attention rows differ only through which query tiles take the
+    # KV-split path - so: bit-identical with the splits off, inside the split-vs-unsplit bound with them on.
+    one = ids[0:1].contiguous()
+    text = torch.arange(2157, 2413, dtype=torch.int32, device="cuda")
+    img = torch.tensor([i for i in range(1100, 2156) if (i - 1100) % 33 != 32], dtype=torch.int32, device="cuda")
+    for ra, rb, win in ((text, None, (2157, 2413)), (text, img, (1100, 2413)), (None, img, (1100, 2156))):
+        kw = dict(rows_a=ra, rows_b=rb, col0_b=126356, ncols_b=8192)
+        try:
+            _lib.lib.mmdp_set_gemm_splitk(0)
+            _lib.check(_lib.lib.mmdp_set_option(b"attn_split_tail", 0))
+            fa, fb = m.forward_rows(one, **kw)
+            wa, wb = m.forward_rows(one, row_window=win, **kw)
+        finally:
+            _lib.lib.mmdp_set_gemm_splitk(2)
+            _lib.check(_lib.lib.mmdp_set_option(b"attn_split_tail", 1))
+        for f, w in ((fa, wa), (fb, wb)):
+            assert (f is None) == (w is None)
+            if f is not None:
+                assert torch.equal(f, w), ("windowed last block must equal the full one", win, float((f.float() - w.float()).abs().max()))
+        fa, fb = m.forward_rows(one, **kw)
+        wa, wb = m.forward_rows(one, row_window=win, **kw)
+        for f, w in ((fa, wa), (fb, wb)):
+            if f is not None:
+                dd = (f.float() - w.float()).abs()
+                sc = f.float().abs().max()
+                assert dd.max() <= 4 * sc * 2.0 ** -8 and dd.mean() <= 0.25 * sc * 2.0 ** -8, (win, float(dd.max()), float(dd.mean()))
+    m.raise_device_errors()
+    # a row outside the window is flagged, not silently served from a stale row
+    m.forward_rows(one, rows_a=text, row_window=(2200, 2413))
+    with pytest.raises(IndexError):
+        m.raise_device_errors()
 
 
 def _device_view_bf16(ptr_value, numel):
