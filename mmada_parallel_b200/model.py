@@ -39,6 +39,27 @@ def rope_tables(head_dim: int, theta: float, seq_len: int) -> Tuple[torch.Tensor
 _BLOCK_KEYS = ("q_proj", "k_proj", "v_proj", "attn_out", "ff_proj", "up_proj", "ff_out", "attn_norm", "ff_norm")
 
 
+def check_supported_config(config, n_heads: int) -> None:
+    """Features of the reference config this path does not implement must fail loudly, not silently differ (shared by the
+    single-GPU and the tensor-parallel model)."""
+    g = lambda k, dflt=None: getattr(config, k, dflt)
+    if g("n_kv_heads") not in (None, n_heads):
+        raise NotImplementedError("GQA/MQA (n_kv_heads != n_heads) is not on the MMaDA-Parallel hot path")
+    for flag in ("alibi", "include_bias", "include_qkv_bias", "weight_tying", "scale_logits", "input_emb_norm",
+                 "attention_layer_norm"):
+        if g(flag, False):
+            raise NotImplementedError(f"config.{flag}=True is not supported by the B200 hot path")
+    if not g("rope", True) or not g("rope_full_precision", True):
+        raise NotImplementedError("the hot path implements full-precision RoPE only")
+    # the kernels implement LLaDALlamaBlock + SwiGLU(silu) + RMSLayerNorm only (modeling_llada.py:906-972, :315-329);
+    # a config that asks for another block / activation / norm must not be computed as if it were this one
+    for key, ok in (("block_type", ("llama",)), ("activation_type", ("silu", "swiglu")), ("layer_norm_type", ("rms",))):
+        v = g(key, None)
+        v = getattr(v, "value", v)  # the reference uses StrEnum members
+        if v is not None and str(v).lower() not in ok:
+            raise NotImplementedError(f"config.{key}={v!r} is not supported by the B200 hot path (needs one of {ok})")
+
+
 class LLaDAForMultiModalGeneration:
     """B200-native drop-in for the reference's inference-time model object (variant A wrapper and, through
     `MMadaModelLM` in mmada.py, variant M)."""
@@ -59,22 +80,7 @@ class LLaDAForMultiModalGeneration:
         self.rope_theta = float(g("rope_theta", 10000.0))
         self.max_seq_len = int(max_seq_len or g("max_sequence_length", 4096))
         self.max_batch = int(max_batch)
-        # features of the reference config this path does not implement must fail loudly, not silently differ
-        if g("n_kv_heads") not in (None, self.n_heads):
-            raise NotImplementedError("GQA/MQA (n_kv_heads != n_heads) is not on the MMaDA-Parallel hot path")
-        for flag in ("alibi", "include_bias", "include_qkv_bias", "weight_tying", "scale_logits", "input_emb_norm",
-                     "attention_layer_norm"):
-            if g(flag, False):
-                raise NotImplementedError(f"config.{flag}=True is not supported by the B200 hot path")
-        if not g("rope", True) or not g("rope_full_precision", True):
-            raise NotImplementedError("the hot path implements full-precision RoPE only")
-        # the kernels implement LLaDALlamaBlock + SwiGLU(silu) + RMSLayerNorm only (modeling_llada.py:906-972, :315-329);
-        # a config that asks for another block / activation / norm must not be computed as if it were this one
-        for key, ok in (("block_type", ("llama",)), ("activation_type", ("silu", "swiglu")), ("layer_norm_type", ("rms",))):
-            v = g(key, None)
-            v = getattr(v, "value", v)  # the reference uses StrEnum members
-            if v is not None and str(v).lower() not in ok:
-                raise NotImplementedError(f"config.{key}={v!r} is not supported by the B200 hot path (needs one of {ok})")
+        check_supported_config(config, self.n_heads)
         cfg = _lib.ModelConfig(self.d_model, self.n_heads, self.n_layers, self.mlp_hidden, self.vocab_rows,
                                self.max_seq_len, self.max_batch, self.rms_eps)
         handle = C.c_void_p()

@@ -30,7 +30,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import EPI_F32, EPI_PLAIN, EPI_SWIGLU, check, lib, ptr, stream_ptr
-from .model import ModelOutput, rope_tables
+from .model import ModelOutput, check_supported_config, rope_tables
 
 
 def shard_state_dict(sd: Dict[str, torch.Tensor], n_layers: int, n_heads: int, rank: int, tp: int, vq_col0: int,
@@ -160,6 +160,7 @@ class TensorParallelLLaDA:
         self.ff = int(g("mlp_hidden_size") or g("mlp_ratio", 4) * self.d_model)
         self.vocab_rows = int(g("embedding_size") or g("vocab_size"))
         self.rms_eps = float(g("rms_norm_eps", 1e-5))
+        check_supported_config(config, self.n_heads)
         self.h_local = self.n_heads // tp_size
         self.d_attn = self.h_local * 128
         if self.d_attn % 256:
