@@ -190,3 +190,35 @@ def test_bench_workload_shapes_and_counts():
     info = bench.host_cpu_info()
     assert 1 <= info["physical_cores"] <= info["logical_cpus"] and isinstance(info["model"], str)
     assert bench.load_peaks()[0] > 100
+
+
+def test_tensor_parallel_chunk_split_and_half_m_unit_schedule():
+    """chunk_split (row chunks of the pipelined tensor-parallel forward): one chunk below 1024 rows, else two chunks that cover
+    [0, M), the first a multiple of 256 rows, chunk 1 never above half the rows (its buffers are sized for that) and every rank owns at
+    least one row of each chunk up to TP=8. And the host restatement of the half-M unit placement of the SwiGLU GEMM
+    (csrc/gemm2.cu: the half unit of n-tile g sits at position (g / period) % num_m, period = clusters / gcd(num_m, clusters)): with
+    unit % clusters as the unit -> cluster map every cluster gets its share of the half units."""
+    from math import gcd
+    from mmada_parallel_b200.tensor_parallel import chunk_split, row_partition
+    assert chunk_split(1023) == [1023] and chunk_split(60) == [60]
+    for M in (1024, 1500, 2341, 2414, 4682, 4828, 4096):
+        parts = chunk_split(M)
+        assert len(parts) == 2 and sum(parts) == M and parts[0] % 256 == 0 and 0 < parts[1] <= (M + 1) // 2
+        for rows in parts:
+            for tp in (2, 4, 8):
+                assert row_partition(rows, tp, tp - 1)[1] >= 1
+    clusters = 74
+    for M, N in ((2414, 24576), (4682, 24576), (2414, 3072 * 2)):
+        num_m, num_n = (M + 255) // 256, N // 256
+        period = clusters // gcd(num_m, clusters)
+        load = [0.0] * clusters
+        halves = [0] * clusters
+        for u in range(num_m * num_n):
+            g, o = divmod(u, num_m)
+            half = o == (g // period) % num_m
+            load[u % clusters] += 0.5 if half else 1.0
+            halves[u % clusters] += half
+        assert sum(halves) == num_n
+        if num_n >= clusters:       # enough half units for everybody: nobody is left with a full extra tile
+            assert min(halves) >= 1
+            assert max(load) <= (num_m * num_n - 0.5 * num_n) / clusters + 0.75
