@@ -587,7 +587,7 @@ def measure_tensor_parallel(args, model_cfg, device, rank, world, replica_model,
         # 2 chunks on two streams: one chunk's NVLink traffic under the other's GEMMs), one sample
         one_chunk_tok_s = None
         main_chunks = int(getattr(tp, "chunks", 1))
-        if True:
+        if getattr(args, "tp_alt_schedule", False):  # opt-in: its numbers are on record (profiles/r02), the default run stays minimal
             tp.chunks, tp._ctx_key = (1 if main_chunks == 2 else 2), None
             dist.barrier()
             torch.cuda.synchronize()
@@ -651,6 +651,8 @@ def main():
                     "baseline, VQ decode timing)")
     ap.add_argument("--variant", default="a", choices=["a", "m"], help="a = BASELINE configs[1] (the contract metric); m = extra line for "
                     "variant M (interleave_generate, CFG batch 2 every step, BASELINE configs[4] per GPU)")
+    ap.add_argument("--tp-alt-schedule", action="store_true", help="tp record: also time one sample with the other row-chunk schedule "
+                    "(two chunks on two streams instead of one)")
     ap.add_argument("--tp-collective", default="p2p", choices=["p2p", "nccl"], help="--tp: fused reduce + residual + norm + broadcast over "
                     "NVLink peer memory (default) or the NCCL all-reduce baseline")
     ap.add_argument("--tp", action="store_true", help="N > 1: ONE sample tensor-parallel over the N GPUs (strong scaling, NCCL "
