@@ -17,7 +17,10 @@
 //   * the S buffers need no "empty" barrier: PV(j) (which waits for P(j), i.e. for the softmax to be done with S(j)) is
 //     issued before QK(j+2) and the tensor core executes one thread's MMAs in order;
 //   * packed-fp32 softmax arithmetic (attention_math.cuh): 3 instructions per score.
-// Measured (B=1, L=2414, H=32): 697 TFLOP/s isolated, 573 TFLOP/s inside the power-capped denoising loop.
+//   * the tiles of a partial last wave are cut along the keys and merged by attention_combine_kernel (see attention_fwd_v6).
+// Measured (B=1, L=2414, H=32, round 2): 1067 TFLOP/s isolated (clocks ~1.6 GHz), 768 TFLOP/s inside the power-capped denoising
+// loop. What bounds it - the ~0.5 us hand-offs between the MMA thread and the softmax warps, twice per block - and why the
+// one-CTA-per-SM arrangement (attention7.cu) does not beat it: DESIGN.md section 5.
 #include "mmdp_internal.h"
 #include "ptx.cuh"
 #include "attention_math.cuh"
