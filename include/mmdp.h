@@ -295,9 +295,9 @@ MMDP_API int mmdp_model_set_rope(mmdp_model* m, const float* cos_tab, const floa
 MMDP_API int mmdp_model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16_t* full_logits, const int32_t* rows_a,
                        int n_a, uint16_t* out_a, const int32_t* rows_b, int n_b, int col0_b, int ncols_b,
                        uint16_t* out_b, void* stream);
-/* The same with a ROW WINDOW for the last block (rows_a / rows_b only, batch 1): nothing after the last block mixes rows, so only
- * rows that are read (all of rows_a / rows_b must lie in [row_lo, row_hi)) need its attention output and MLP; keys and values of all
- * rows are still computed. Output-invariant dead-work elimination (identical GEMM results per row; the attention rows differ
+/* The same with a ROW WINDOW for the last block (rows_a / rows_b only): nothing after the last block mixes rows, so only rows that
+ * are read (every index of rows_a / rows_b must be a position in [row_lo, row_hi) of its batch row: (index % L) inside the window)
+ * need its attention output and MLP; keys and values of all rows are still computed; one launch set per batch row. Output-invariant dead-work elimination (identical GEMM results per row; the attention rows differ
  * from the unwindowed launch only by which query tiles take the KV-split path). A row index outside the window raises bit 2 of the
  * error flags (mmdp_model_error_flags). row_hi <= row_lo disables the window. */
 MMDP_API int mmdp_model_forward_window(mmdp_model* m, const int64_t* ids, int B, int L, const int32_t* rows_a, int n_a, uint16_t* out_a,

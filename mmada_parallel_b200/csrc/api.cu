@@ -474,22 +474,32 @@ static int model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16
     if (embed_rows(ids, m->wte, m->x, M, d, V, s, m->err_flag)) return -1;
     QkvRopeArgs qa{m->q, m->k, m->vt, m->cos_tab, m->sin_tab, L, Lpad, d, H};
     // Row window of the LAST block: nothing after the last block mixes rows (ln_f and the LM head are row-wise and only the rows in
-    // rows_a / rows_b are read), so its query rows / attn_out / MLP outside [row_lo, row_hi) are dead work: the keys and values of
-    // ALL rows are still computed, the rest of the block runs on the window only. Batch 1 (the window is one row range).
-    const bool window = !full_logits && B == 1 && row_hi > row_lo && row_lo >= 0 && row_hi <= M && (row_hi - row_lo) < M;
-    if (!window) { row_lo = 0; row_hi = M; }
+    // rows_a / rows_b are read), so its query rows / attn_out / MLP outside positions [row_lo, row_hi) of every batch row are dead
+    // work: the keys and values of ALL rows are still computed, the rest of the block runs on the window only (per batch row).
+    const bool window = !full_logits && row_hi > row_lo && row_lo >= 0 && row_hi <= L && (row_hi - row_lo) < L;
+    if (!window) { row_lo = 0; row_hi = L; }
     for (int li = 0; li < c.n_layers; ++li) {
         const LayerWeights& l = m->layers[li];
         const bool win = window && li == c.n_layers - 1;
-        const int r0 = win ? row_lo : 0, Mw = win ? row_hi - row_lo : M;
-        const size_t o_d = (size_t)r0 * d, o_ff = (size_t)r0 * ff;
         if (rmsnorm(m->x, d, l.attn_norm, m->xn, d, M, d, c.rms_eps, s)) return -1;
         if (gemm_bf16(EPI_QKVROPE, m->xn, d, l.wqkv, d, M, 3 * d, d, nullptr, 0, nullptr, 0, &qa, s)) return -1;
-        if (attention_fwd(m->q + o_d, m->k, m->vt, m->att + o_d, B, H, L, Lpad, scale, s, win ? Mw : 0)) return -1;
-        if (gemm_bf16(EPI_RESID, m->att + o_d, d, l.wo, d, Mw, d, d, m->x + o_d, d, m->x + o_d, d, nullptr, s)) return -1;
-        if (rmsnorm(m->x + o_d, d, l.ff_norm, m->xn + o_d, d, Mw, d, c.rms_eps, s)) return -1;
-        if (gemm_bf16(EPI_SWIGLU, m->xn + o_d, d, l.w13, d, Mw, 2 * ff, d, m->h + o_ff, ff, nullptr, 0, nullptr, s)) return -1;
-        if (gemm_bf16(EPI_RESID, m->h + o_ff, ff, l.w2, ff, Mw, d, ff, m->x + o_d, d, m->x + o_d, d, nullptr, s)) return -1;
+        if (!win) {
+            if (attention_fwd(m->q, m->k, m->vt, m->att, B, H, L, Lpad, scale, s)) return -1;
+            if (gemm_bf16(EPI_RESID, m->att, d, l.wo, d, M, d, d, m->x, d, m->x, d, nullptr, s)) return -1;
+            if (rmsnorm(m->x, d, l.ff_norm, m->xn, d, M, d, c.rms_eps, s)) return -1;
+            if (gemm_bf16(EPI_SWIGLU, m->xn, d, l.w13, d, M, 2 * ff, d, m->h, ff, nullptr, 0, nullptr, s)) return -1;
+            if (gemm_bf16(EPI_RESID, m->h, ff, l.w2, ff, M, d, ff, m->x, d, m->x, d, nullptr, s)) return -1;
+            continue;
+        }
+        const int Mw = row_hi - row_lo;
+        for (int b = 0; b < B; ++b) {  // one row range per batch row (B = 1, or the CFG batch of variant M)
+            const size_t r0 = (size_t)b * L + row_lo, o_d = r0 * d, o_ff = r0 * ff;
+            if (attention_fwd(m->q + o_d, m->k + (size_t)b * L * d, m->vt + (size_t)b * H * 128 * Lpad, m->att + o_d, 1, H, L, Lpad, scale, s, Mw)) return -1;
+            if (gemm_bf16(EPI_RESID, m->att + o_d, d, l.wo, d, Mw, d, d, m->x + o_d, d, m->x + o_d, d, nullptr, s)) return -1;
+            if (rmsnorm(m->x + o_d, d, l.ff_norm, m->xn + o_d, d, Mw, d, c.rms_eps, s)) return -1;
+            if (gemm_bf16(EPI_SWIGLU, m->xn + o_d, d, l.w13, d, Mw, 2 * ff, d, m->h + o_ff, ff, nullptr, 0, nullptr, s)) return -1;
+            if (gemm_bf16(EPI_RESID, m->h + o_ff, ff, l.w2, ff, Mw, d, ff, m->x + o_d, d, m->x + o_d, d, nullptr, s)) return -1;
+        }
     }
     if (full_logits) {
         if (rmsnorm(m->x, d, m->ln_f, m->xn, d, M, d, c.rms_eps, s)) return -1;
@@ -498,14 +508,14 @@ static int model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16
     if (n_a > 0) {
         if (!rows_a || !out_a) return set_error("mmdp_model_forward: rows_a/out_a null");
         if (n_a > m->Mmax) return set_error("mmdp_model_forward: too many rows_a");
-        if (rmsnorm_rows(m->x, d, rows_a, m->ln_f, m->xr, d, n_a, d, c.rms_eps, s, M, m->err_flag, row_lo, row_hi)) return -1;
+        if (rmsnorm_rows(m->x, d, rows_a, m->ln_f, m->xr, d, n_a, d, c.rms_eps, s, M, m->err_flag, window ? row_lo : 0, window ? row_hi : 0, window ? L : 0)) return -1;
         if (gemm_bf16(EPI_PLAIN, m->xr, d, m->head, d, n_a, V, d, (bf16*)out_a, V, nullptr, 0, nullptr, s)) return -1;
     }
     if (n_b > 0) {
         if (!rows_b || !out_b) return set_error("mmdp_model_forward: rows_b/out_b null");
         if (n_a + n_b > m->Mmax) return set_error("mmdp_model_forward: too many rows_a + rows_b");
         bf16* xr_b = m->xr + (size_t)n_a * d;
-        if (rmsnorm_rows(m->x, d, rows_b, m->ln_f, xr_b, d, n_b, d, c.rms_eps, s, M, m->err_flag, row_lo, row_hi)) return -1;
+        if (rmsnorm_rows(m->x, d, rows_b, m->ln_f, xr_b, d, n_b, d, c.rms_eps, s, M, m->err_flag, window ? row_lo : 0, window ? row_hi : 0, window ? L : 0)) return -1;
         if (gemm_bf16(EPI_PLAIN, xr_b, d, m->head + (size_t)col0_b * d, d, n_b, ncols_b, d, (bf16*)out_b, ncols_b, nullptr, 0, nullptr, s)) return -1;
     }
     return 0;

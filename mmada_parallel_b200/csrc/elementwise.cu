@@ -37,7 +37,7 @@ int embed_rows(const int64_t* ids, const __nv_bfloat16* wte, __nv_bfloat16* x, i
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int d, float eps, int src_rows,
-               int* __restrict__ err, int row_lo, int row_hi) {
+               int* __restrict__ err, int row_lo, int row_hi, int row_mod) {
     const int orow = blockIdx.x;
     pdl_launch_dependents();
     pdl_wait();
@@ -45,7 +45,7 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restri
     if (rows && (irow < 0 || irow >= src_rows)) {  // gather index outside the source matrix: flag it, read row 0
         if (err && threadIdx.x == 0) atomicOr(err, 2);
         irow = 0;
-    } else if (rows && (irow < row_lo || irow >= row_hi)) {  // a row the last block was not computed for (row window of the forward)
+    } else if (rows && ((irow % row_mod) < row_lo || (irow % row_mod) >= row_hi)) {  // a row the last block was not computed for (row window of every batch row)
         if (err && threadIdx.x == 0) atomicOr(err, 4);
     }
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)irow * ldx);
@@ -128,7 +128,7 @@ template <int NV>
 __global__ void __launch_bounds__(256, 2)
 rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __restrict__ rows,
                     const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int ldy, int M, float eps, int src_rows,
-                    int* __restrict__ err, int row_lo, int row_hi) {
+                    int* __restrict__ err, int row_lo, int row_hi, int row_mod) {
     const int orow = blockIdx.x * 8 + (threadIdx.x >> 5);
     pdl_launch_dependents();
     pdl_wait();
@@ -138,7 +138,7 @@ rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __r
     if (rows && (irow < 0 || irow >= src_rows)) {  // gather index outside the source matrix: flag it, read row 0
         if (err && lane == 0) atomicOr(err, 2);
         irow = 0;
-    } else if (rows && (irow < row_lo || irow >= row_hi)) {  // a row the last block was not computed for (row window of the forward)
+    } else if (rows && ((irow % row_mod) < row_lo || (irow % row_mod) >= row_hi)) {  // a row the last block was not computed for (row window of every batch row)
         if (err && lane == 0) atomicOr(err, 4);
     }
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)irow * ldx);
@@ -197,8 +197,8 @@ rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int* __r
 }
 
 int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
-                 int M, int d, float eps, cudaStream_t stream, int src_rows, int* err, int row_lo, int row_hi) {
-    if (row_hi <= 0) { row_lo = 0; row_hi = src_rows; }
+                 int M, int d, float eps, cudaStream_t stream, int src_rows, int* err, int row_lo, int row_hi, int row_mod) {
+    if (row_hi <= 0 || row_mod <= 0) { row_lo = 0; row_hi = 0x7fffffff; row_mod = 0x7fffffff; }
     if (M <= 0) return 0;
     if ((d % 8) || (ldx % 8) || (ldy % 8)) return set_error("rmsnorm: d/ldx/ldy must be multiples of 8");
     LaunchScope ls(LK_ROW, 2.0 * M * (double)d * 2, stream);  // bytes: read x + write y
@@ -207,12 +207,12 @@ int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bf
     const bool pdl = pdl_mode() != 0;
     cudaError_t e;
     switch (use_warp ? d : -1) {  // warp-per-row variants for the model widths in use; anything else takes the CTA-per-row kernel
-        case 4096: e = launch_ex(rmsnorm_warp_kernel<16>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi); break;
-        case 2048: e = launch_ex(rmsnorm_warp_kernel<8>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi); break;
-        case 1024: e = launch_ex(rmsnorm_warp_kernel<4>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi); break;
-        case 512: e = launch_ex(rmsnorm_warp_kernel<2>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi); break;
-        case 256: e = launch_ex(rmsnorm_warp_kernel<1>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi); break;
-        default: e = launch_ex(rmsnorm_kernel, dim3(M), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, d, eps, src_rows, err, row_lo, row_hi);
+        case 4096: e = launch_ex(rmsnorm_warp_kernel<16>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi, row_mod); break;
+        case 2048: e = launch_ex(rmsnorm_warp_kernel<8>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi, row_mod); break;
+        case 1024: e = launch_ex(rmsnorm_warp_kernel<4>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi, row_mod); break;
+        case 512: e = launch_ex(rmsnorm_warp_kernel<2>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi, row_mod); break;
+        case 256: e = launch_ex(rmsnorm_warp_kernel<1>, dim3(grid8), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, M, eps, src_rows, err, row_lo, row_hi, row_mod); break;
+        default: e = launch_ex(rmsnorm_kernel, dim3(M), dim3(256), 0, stream, pdl, false, x, ldx, rows, w, y, ldy, d, eps, src_rows, err, row_lo, row_hi, row_mod);
     }
     MMDP_CUDA(e);
     MMDP_CUDA(cudaGetLastError());

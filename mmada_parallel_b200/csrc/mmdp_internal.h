@@ -138,7 +138,7 @@ int rmsnorm(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* w, __nv_bfloat
 int resid_add_f32(__nv_bfloat16* x, int ldx, const float* partial, int ldp, int M, int d, cudaStream_t stream);
 // src_rows / err: gather indices outside [0, src_rows) raise bit 1 of *err (nullable) and read row 0
 int rmsnorm_rows(const __nv_bfloat16* x, int ldx, const int* rows, const __nv_bfloat16* w, __nv_bfloat16* y, int ldy,
-                 int M, int d, float eps, cudaStream_t stream, int src_rows = 0x7fffffff, int* err = nullptr, int row_lo = 0, int row_hi = 0);
+                 int M, int d, float eps, cudaStream_t stream, int src_rows = 0x7fffffff, int* err = nullptr, int row_lo = 0, int row_hi = 0, int row_mod = 0);
 
 int text_step(const __nv_bfloat16* cond, const __nv_bfloat16* uncond, int64_t ld, int R, int V, float text_cfg,
               const __nv_bfloat16* unoise, int64_t ld_noise, float temperature, int64_t* ids_text, int64_t mask_id,

@@ -93,10 +93,14 @@ class MMadaModelLM(LLaDAForMultiModalGeneration):
         unk_ws = torch.empty(n_vq, dtype=torch.uint8, device=dev)
         noise = _Noise(generator, dev)
         any_image_step = False
+        # positions whose logits are read, per batch row: the last block computes its attention output / MLP for them only
+        # (model.forward_rows, row_window; long sequences only - the tiny parity models keep one fixed kernel schedule)
+        win_text, win_img = ((t0, L), (P + 1, L)) if L >= 1024 else (None, None)
         for i in range(text_steps):
             is_img = i in img_idx
             self.forward_rows(both, rows_a=rows_text, out_a=text_logits, rows_b=rows_img if is_img else None,
-                              col0_b=tvoc, ncols_b=C, out_b=img_logits if is_img else None)     # :172
+                              col0_b=tvoc, ncols_b=C, out_b=img_logits if is_img else None,
+                              row_window=win_img if is_img else win_text)                       # :172
             # text step on the CFG-mixed logits (:179-209); only the cond row's ids change ...
             if text_temperature != 0:
                 # add_gumbel_noise (:49-60): fp64 uniform noise of the text-logits shape from the GLOBAL RNG of the logits'

@@ -283,9 +283,9 @@ class LLaDAForMultiModalGeneration:
                      out_b: Optional[torch.Tensor] = None, row_window: Optional[tuple] = None):
         """One forward over ids [B, L] (cuda int64). rows_* are int32 flattened row indices b*L + pos.
         Returns (logits_a [n_a, V] or None, logits_b [n_b, ncols_b] or None).
-        row_window = (lo, hi), batch 1: every row index lies in [lo, hi) - the last block then computes its attention output and
-        MLP for that row range only (keys / values for all rows): nothing after it mixes rows, the skipped rows are never read.
-        A row outside the window raises IndexError at the next raise_device_errors()."""
+        row_window = (lo, hi): every requested row is a position in [lo, hi) of its batch row - the last block then computes its
+        attention output and MLP for those positions only (keys / values for all rows): nothing after it mixes rows, the skipped
+        rows are never read. A row outside the window raises IndexError at the next raise_device_errors()."""
         B, L = ids.shape
         n_a = 0 if rows_a is None else rows_a.numel()
         n_b = 0 if rows_b is None else rows_b.numel()
@@ -293,7 +293,7 @@ class LLaDAForMultiModalGeneration:
             out_a = torch.empty((n_a, self.vocab_rows), dtype=torch.bfloat16, device=self.device)
         if n_b and out_b is None:
             out_b = torch.empty((n_b, ncols_b), dtype=torch.bfloat16, device=self.device)
-        lo, hi = (int(row_window[0]), int(row_window[1])) if (row_window is not None and B == 1) else (0, 0)
+        lo, hi = (int(row_window[0]), int(row_window[1])) if row_window is not None else (0, 0)
         check(lib.mmdp_model_forward_window(self._h, ptr(ids), B, L, ptr(rows_a), n_a, ptr(out_a) if n_a else None,
                                             ptr(rows_b), n_b, col0_b, ncols_b, ptr(out_b) if n_b else None, lo, hi, stream_ptr()))
         return (out_a if n_a else None), (out_b if n_b else None)

@@ -237,6 +237,17 @@ def test_full_size_properties():
                 dd = (f.float() - w.float()).abs()
                 sc = f.float().abs().max()
                 assert dd.max() <= 4 * sc * 2.0 ** -8 and dd.mean() <= 0.5 * sc * 2.0 ** -8, (win, float(dd.max()), float(dd.mean()))
+    # the CFG batch of variant M: the same window in both batch rows
+    rows2 = torch.cat([text, text + L]).contiguous()
+    try:
+        _lib.lib.mmdp_set_gemm_splitk(0)
+        _lib.check(_lib.lib.mmdp_set_option(b"attn_split_tail", 0))
+        f2, _ = m.forward_rows(ids, rows_a=rows2)
+        w2, _ = m.forward_rows(ids, rows_a=rows2, row_window=(2157, 2413))
+    finally:
+        _lib.lib.mmdp_set_gemm_splitk(2)
+        _lib.check(_lib.lib.mmdp_set_option(b"attn_split_tail", 1))
+    assert torch.equal(f2, w2), float((f2.float() - w2.float()).abs().max())
     m.raise_device_errors()
     # a row outside the window is flagged, not silently served from a stale row
     m.forward_rows(one, rows_a=text, row_window=(2200, 2413))
