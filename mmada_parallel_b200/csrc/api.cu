@@ -476,7 +476,7 @@ static int model_forward(mmdp_model* m, const int64_t* ids, int B, int L, uint16
     // Row window of the LAST block: nothing after the last block mixes rows (ln_f and the LM head are row-wise and only the rows in
     // rows_a / rows_b are read), so its query rows / attn_out / MLP outside positions [row_lo, row_hi) of every batch row are dead
     // work: the keys and values of ALL rows are still computed, the rest of the block runs on the window only (per batch row).
-    const bool window = !full_logits && row_hi > row_lo && row_lo >= 0 && row_hi <= L && (row_hi - row_lo) < L;
+    const bool window = !full_logits && opt(OPT_ROW_WINDOW) && row_hi > row_lo && row_lo >= 0 && row_hi <= L && (row_hi - row_lo) < L;  // MMDP_ROW_WINDOW=0: A/B switch
     if (!window) { row_lo = 0; row_hi = L; }
     for (int li = 0; li < c.n_layers; ++li) {
         const LayerWeights& l = m->layers[li];

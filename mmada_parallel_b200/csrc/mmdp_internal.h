@@ -34,7 +34,7 @@ void set_pdl_mode(int on);
 int env_int(const char* name, int dflt);
 // tuning options (runtime.cu): environment default, mmdp_set_option(key, value) at run time
 enum OptId { OPT_PDL = 0, OPT_GEMM_SPLITK, OPT_GEMM_L2PF, OPT_GEMM_L2PF_MOD, OPT_GEMM_PAIR, OPT_GEMM_GROUP_M, OPT_ATTN_SPLIT_TAIL,
-             OPT_ATTN_POLY, OPT_RMSNORM_WARP, OPT_GEMM_NSPLIT_TAIL, OPT_ATTN_VERSION, OPT_ATTN_PROBE, OPT_GEMM_MTAIL, OPT_COUNT };
+             OPT_ATTN_POLY, OPT_RMSNORM_WARP, OPT_GEMM_NSPLIT_TAIL, OPT_ATTN_VERSION, OPT_ATTN_PROBE, OPT_GEMM_MTAIL, OPT_ROW_WINDOW, OPT_COUNT };
 int opt(int id);
 int set_opt(const char* key, int value);
 

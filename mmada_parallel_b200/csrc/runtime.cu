@@ -56,6 +56,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"attn_version", "MMDP_ATTN_VERSION", 6, 0, false},
     {"attn_probe", "MMDP_ATTN_PROBE", 0, 0, false},
     {"gemm_mtail", "MMDP_GEMM_MTAIL", 1, 0, false},
+    {"row_window", "MMDP_ROW_WINDOW", 1, 0, false},
 };
 int opt(int id) {
     Opt& o = g_opts[id];
